@@ -1,0 +1,147 @@
+"""ctypes binding of ``libmmf_b200.so`` (the C ABI in ``include/mmf_b200.h``).
+
+No torch types cross this boundary: tensors are passed as raw device pointers plus sizes, the
+stream as a ``cudaStream_t`` integer.  There is NO fallback: if the shared library is missing or
+the device is not sm_100, every entry point raises.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmf_b200.so")
+
+MAX_SD, MAX_CD, MAX_HEADS, UNITS = 4, 16, 4, 64
+
+RESAMPLE_NONE = 0
+RESAMPLE_MULTINOMIAL_STRICT = 1
+RESAMPLE_MULTINOMIAL_FAST = 2
+RESAMPLE_SYSTEMATIC_STRICT = 3
+RESAMPLE_SYSTEMATIC_FAST = 4
+ESTIMATE_WEIGHTED_AVERAGE = 0
+ESTIMATE_ARGMAX = 1
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+
+
+class Chain(C.Structure):
+    _fields_ = [
+        ("in_dim", C.c_int32),
+        ("n_pre_res", C.c_int32),
+        ("mid_relu", C.c_int32),
+        ("n_post_res", C.c_int32),
+        ("out_dim", C.c_int32),
+        ("reserved", C.c_int32),
+        ("w", C.c_void_p),
+        ("w_mma", C.c_void_p),
+    ]
+
+
+class TrajRows(C.Structure):
+    _fields_ = [("in_dim", C.c_int32), ("has_encoder", C.c_int32), ("w", C.c_void_p)]
+
+
+class PFModel(C.Structure):
+    _fields_ = [
+        ("state_dim", C.c_int32),
+        ("control_dim", C.c_int32),
+        ("num_heads", C.c_int32),
+        ("reserved", C.c_int32),
+        ("dynamics", Chain),
+        ("dynamics_rows", TrajRows),
+        ("heads", Chain * MAX_HEADS),
+        ("head_rows", TrajRows * MAX_HEADS),
+        ("q_tril", C.c_float * (MAX_SD * MAX_SD)),
+    ]
+
+
+class EKFModel(C.Structure):
+    _fields_ = [
+        ("state_dim", C.c_int32),
+        ("control_dim", C.c_int32),
+        ("dynamics", Chain),
+        ("dynamics_rows", TrajRows),
+        ("q_tril", C.c_float * (MAX_SD * MAX_SD)),
+    ]
+
+
+class MMFError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+_i32, _f32, _u32, _vp, _sz = C.c_int32, C.c_float, C.c_uint32, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); also the list of symbols tests check against the header
+PROTOTYPES = {
+    "mmf_last_error": (C.c_char_p, []),
+    "mmf_abi_version": (C.c_int, []),
+    "mmf_device_check": (C.c_int, []),
+    "mmf_pf_init": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_pf_traj_rows": (C.c_int, [C.POINTER(PFModel), _i32, _vp, C.POINTER(_vp), _vp, _vp]),
+    "mmf_pf_predict_measure": (
+        C.c_int,
+        [C.POINTER(PFModel), _i32, _i32, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp],
+    ),
+    "mmf_pf_resample_workspace_bytes": (_sz, [_i32, _i32]),
+    "mmf_pf_normalize_resample": (
+        C.c_int,
+        [_i32, _i32, _i32, _vp, _vp, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    ),
+    "mmf_fuse_loglik": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "mmf_resample": (C.c_int, [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "mmf_ekf_loop_fwd": (C.c_int, [C.POINTER(EKFModel), _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_dynamics_jacobian": (C.c_int, [C.POINTER(EKFModel), _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_kf_fuse_crossmodal": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_kf_fuse_unimodal": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_chain_mma_bytes": (_sz, [C.POINTER(Chain)]),
+    "mmf_pack_chain_mma": (C.c_int, [C.POINTER(Chain), _vp, _vp]),
+}
+
+
+def load():
+    """Load the shared library (once).  Raises MMFError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise MMFError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C multimodalfilter_b200/csrc`).  There is no CPU or eager fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.mmf_abi_version() != 1:
+            raise MMFError(f"ABI mismatch: library reports version {lib.mmf_abi_version()}, binding expects 1")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().mmf_last_error()
+        raise MMFError(f"libmmf_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise MMFError("libmmf_b200 only takes CUDA tensors: there is no CPU path")
+    if not t.is_contiguous():
+        raise MMFError("libmmf_b200 needs C-contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_of(t):
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)

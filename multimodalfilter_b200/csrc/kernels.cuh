@@ -1,0 +1,58 @@
+// kernels.cuh -- parameter blocks and launchers shared between the translation units.
+#pragma once
+#include "common.cuh"
+
+namespace mmf {
+
+struct ResampleParams {
+  int N, M, sd, M_out;
+  int estimation, mode;
+  float alpha;
+  const float* states;
+  const float* logw_unnorm;  // ignored when logits_in != null
+  const float* logits_in;    // standalone mmf_resample(): logits given directly
+  const double* uniforms;
+  float* states_out;
+  float* logw_out;
+  float* est_out;
+  float* logw_norm_out;
+  float* logits_out;
+  long long* idx_out;
+};
+
+constexpr int EKF_MAX_FILTERS = 4;
+constexpr int EKF_MAX_WARPS = 16;
+
+struct EkfParams {
+  ChainDev dyn[EKF_MAX_FILTERS];
+  TrajRowsDev rows[EKF_MAX_FILTERS];
+  float q[EKF_MAX_FILTERS][MMF_MAX_SD * MMF_MAX_SD];
+  int F, T, N, cd, jac_only;
+  const float* mean0;     // (F, N, sd)
+  const float* cov0;      // (F, N, sd, sd)
+  const float* controls;  // (T, N, cd)   shared by all filters
+  const float* z;         // (F, T, N, sd)
+  const float* r_tril;    // (F, T, N, sd, sd)
+  float* mean_out;        // (F, T, N, sd)      [jac_only: pred (N, sd)]
+  float* cov_out;         // (F, T, N, sd, sd)  [jac_only: jacobian (N, sd, sd)]
+};
+
+int launch_particle_chain_ffma(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
+                               const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
+                               float* states_out, float* logw_out, float* ll_out, cudaStream_t stream);
+int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
+                             const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
+                             int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream);
+int launch_traj_rows(const mmf_pf_model* model, int N, const float* controls, const float* const* obs_feats,
+                     float* out, cudaStream_t stream);
+int launch_fuse_loglik(int N, int M, int K, const float* ll, const float* w, float* out, cudaStream_t stream);
+int launch_pf_init(int N, int M, int sd, const float* mean, const float* cov, const float* eps, float* states,
+                   float* logw, cudaStream_t stream);
+int launch_normalize_resample(const ResampleParams& P, cudaStream_t stream);
+int launch_ekf(const EkfParams& P, int sd, cudaStream_t stream);
+int launch_kf_fuse(int K, long long rows, int sd, const float* mu, const float* Pk, const float* beta,
+                   float* mean_out, float* cov_out, int unimodal, cudaStream_t stream);
+size_t chain_mma_bytes(const mmf_chain* chain);
+int pack_chain_mma(const mmf_chain* chain, void* dst, cudaStream_t stream);
+
+}  // namespace mmf

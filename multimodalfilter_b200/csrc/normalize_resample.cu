@@ -1,0 +1,332 @@
+// normalize_resample.cu -- second half of R6 (normalise, estimate) and R7 (resample + gather).
+// HBM-bound: per particle it reads logw (4 B) + state (4*sd B) [+ uniform 8 B] and writes the
+// resampled state (4*sd B) + log-weight (4 B) [+ index 8 B].
+//
+// One CTA per trajectory; the trajectory's log-weights / CDF live in shared memory.
+// Replaces A.3 `logw - logsumexp`, `sum(exp(logw) * states)`, `_resample()` (Categorical.sample
+// -> torch.multinomial inverse CDF -> gather); call site ref: crossmodal/eval_helpers.py:139-142.
+//
+// Resampling arithmetic is PINNED: max is exact; e_j = exp_pinned(l_j - max);
+//   *_STRICT: c_j = sequential fp32 running sum (what torch.multinomial does on CPU, A.6);
+//   *_FAST  : segments of 8 (serial) -> groups of 32 segments (Kogge-Stone over segment totals)
+//             -> serial over group totals; c_j = (G_excl[g] + S_excl[s]) + local_j;
+//   idx = lower_bound over fl(c_j / c_{M-1}) compared as double with u; clamped to M-1.
+#include "kernels.cuh"
+#include "pinned_math.cuh"
+
+namespace mmf {
+
+constexpr int NR_TPB = 256;
+constexpr int SEG = 8;
+constexpr int GROUP = 32 * SEG;
+
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  float r = scratch[0];
+  for (int w = 1; w < NR_TPB / 32; ++w) r = fmaxf(r, scratch[w]);
+  return r;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  float r = scratch[0];
+  for (int w = 1; w < NR_TPB / 32; ++w) r += scratch[w];
+  return r;
+}
+
+__device__ __forceinline__ int lower_bound_cdf(const float* cdf, int M, float total, double u) {
+  int lo = 0, hi = M;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    const float c = __fdiv_rn(cdf[mid], total);
+    if ((double)c < u) lo = mid + 1; else hi = mid;
+  }
+  return lo < M - 1 ? lo : M - 1;
+}
+
+__global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_constant__ ResampleParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int M = P.M, sd = P.sd, tid = threadIdx.x;
+  const int Mpad = ((M + GROUP - 1) / GROUP) * GROUP;
+  float* scratch = sm;            // 32
+  float* cdf = sm + 32;           // Mpad   (log-weights first, CDF later)
+  float* segoff = cdf + Mpad;     // Mpad / SEG
+  float* gtot = segoff + Mpad / SEG;  // Mpad / GROUP (+1)
+  float* diff = gtot + Mpad / GROUP + 4;  // M (only when alpha < 1): logw - logits
+  const bool soft = P.alpha < 1.0f;
+  const bool resample = P.mode != MMF_RESAMPLE_NONE;
+
+  for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
+    __syncthreads();
+    float lmax;
+    if (P.logits_in == nullptr) {
+      // ---- normalise: logw = l - logsumexp(l) ----------------------------------------------------
+      const float* lw = P.logw_unnorm + (size_t)n * M;
+      float mx = -INFINITY;
+      for (int i = tid; i < M; i += NR_TPB) {
+        const float l = lw[i];
+        cdf[i] = l;
+        mx = fmaxf(mx, l);
+      }
+      mx = block_max(mx, scratch);
+      const float shift = (mx == -INFINITY || mx == INFINITY) ? 0.0f : mx;
+      float s = 0.0f;
+      for (int i = tid; i < M; i += NR_TPB) s += expf(cdf[i] - shift);
+      s = block_sum(s, scratch);
+      const float lse = shift + logf(s);
+
+      // ---- estimate ------------------------------------------------------------------------------
+      const float* xs = P.states + (size_t)n * M * sd;
+      float acc[MMF_MAX_SD] = {0.f, 0.f, 0.f, 0.f};
+      float best = -INFINITY;
+      int best_i = 0x7fffffff;
+      for (int i = tid; i < M; i += NR_TPB) {
+        const float l = cdf[i] - lse;
+        cdf[i] = l;
+        if (P.logw_norm_out) P.logw_norm_out[(size_t)n * M + i] = l;
+        if (!resample) P.logw_out[(size_t)n * M + i] = l;
+        if (P.estimation == MMF_ESTIMATE_WEIGHTED_AVERAGE) {
+          const float wgt = expf(l);
+#pragma unroll
+          for (int d = 0; d < MMF_MAX_SD; ++d)
+            if (d < sd) acc[d] = fmaf(wgt, xs[(size_t)i * sd + d], acc[d]);
+        } else if (l > best) {
+          best = l;
+          best_i = i;
+        }
+      }
+      if (P.estimation == MMF_ESTIMATE_WEIGHTED_AVERAGE) {
+#pragma unroll
+        for (int d = 0; d < MMF_MAX_SD; ++d) {
+          if (d < sd) {
+            const float v = block_sum(acc[d], scratch);
+            if (tid == 0) P.est_out[(size_t)n * sd + d] = v;
+          }
+        }
+      } else {
+        const float gbest = block_max(best, scratch);
+        int cand = (best == gbest) ? best_i : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        __shared__ int cand_w[NR_TPB / 32];
+        __syncthreads();
+        if ((tid & 31) == 0) cand_w[tid >> 5] = cand;
+        __syncthreads();
+        int win = cand_w[0];
+        for (int w = 1; w < NR_TPB / 32; ++w) win = min(win, cand_w[w]);
+        if (win == 0x7fffffff) win = 0;
+        if (tid < sd) P.est_out[(size_t)n * sd + tid] = xs[(size_t)win * sd + tid];
+      }
+      if (!resample) continue;
+
+      // ---- logits (soft resampling mixes in the uniform, A.3) ------------------------------------
+      float lm = -INFINITY;
+      if (soft) {
+        const float la = logf(P.alpha), lb = -logf((float)M) + logf(1.0f - P.alpha);
+        for (int i = tid; i < M; i += NR_TPB) {
+          const float a = cdf[i] + la;
+          const float m2 = fmaxf(a, lb);
+          const float lg = m2 + logf(expf(a - m2) + expf(lb - m2));
+          diff[i] = cdf[i] - lg;
+          cdf[i] = lg;
+          lm = fmaxf(lm, lg);
+        }
+      } else {
+        for (int i = tid; i < M; i += NR_TPB) lm = fmaxf(lm, cdf[i]);
+      }
+      lmax = block_max(lm, scratch);
+    } else {
+      const float* lg = P.logits_in + (size_t)n * M;
+      float lm = -INFINITY;
+      for (int i = tid; i < M; i += NR_TPB) {
+        const float l = lg[i];
+        cdf[i] = l;
+        lm = fmaxf(lm, l);
+      }
+      lmax = block_max(lm, scratch);
+    }
+    if (P.logits_out)
+      for (int i = tid; i < M; i += NR_TPB) P.logits_out[(size_t)n * M + i] = cdf[i];
+
+    // ---- pinned softmax numerators ------------------------------------------------------------------
+    for (int i = tid; i < Mpad; i += NR_TPB) cdf[i] = (i < M) ? exp_pinned(cdf[i] - lmax) : 0.0f;
+    __syncthreads();
+
+    // ---- CDF --------------------------------------------------------------------------------------------
+    const bool strict = (P.mode == MMF_RESAMPLE_MULTINOMIAL_STRICT || P.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT);
+    if (strict) {
+      if (tid == 0) {
+        float run = 0.0f;
+        for (int i = 0; i < M; ++i) {
+          run = __fadd_rn(run, cdf[i]);
+          cdf[i] = run;
+        }
+      }
+      __syncthreads();
+    } else {
+      const int lane = tid & 31, wid = tid >> 5;
+      const int groups = Mpad / GROUP;
+      for (int g = wid; g < groups; g += NR_TPB / 32) {
+        const int s = g * 32 + lane;
+        float* e = cdf + (size_t)s * SEG;
+        float run = 0.0f;
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) {
+          run = __fadd_rn(run, e[i]);
+          e[i] = run;
+        }
+        float t = run;  // Kogge-Stone inclusive scan of the 32 segment totals
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float v = __shfl_up_sync(0xffffffffu, t, d);
+          if (lane >= d) t = __fadd_rn(v, t);
+        }
+        const float excl = __shfl_up_sync(0xffffffffu, t, 1);
+        segoff[s] = (lane == 0) ? 0.0f : excl;
+        if (lane == 31) gtot[g] = t;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float run = 0.0f;
+        for (int g = 0; g < groups; ++g) {
+          const float t = gtot[g];
+          gtot[g] = run;  // exclusive
+          run = __fadd_rn(run, t);
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < M; i += NR_TPB) {
+        const float base = __fadd_rn(gtot[i / GROUP], segoff[i / SEG]);
+        cdf[i] = __fadd_rn(base, cdf[i]);
+      }
+      __syncthreads();
+    }
+    const float total = cdf[M - 1];
+
+    // ---- inverse CDF + gather -----------------------------------------------------------------------
+    const bool systematic = (P.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT || P.mode == MMF_RESAMPLE_SYSTEMATIC_FAST);
+    const float uniform_lw = -logf((float)M);
+    const double u0 = systematic ? P.uniforms[n] : 0.0;
+    for (int j = tid; j < P.M_out; j += NR_TPB) {
+      const double u = systematic ? (u0 + (double)j) / (double)P.M_out
+                                  : P.uniforms[(size_t)n * P.M_out + j];
+      const int idx = lower_bound_cdf(cdf, M, total, u);
+      if (P.idx_out) P.idx_out[(size_t)n * P.M_out + j] = idx;
+      if (P.states_out) {
+        const float* src = P.states + ((size_t)n * M + idx) * sd;
+        float* dst = P.states_out + ((size_t)n * P.M_out + j) * sd;
+#pragma unroll
+        for (int d = 0; d < MMF_MAX_SD; ++d)
+          if (d < sd) dst[d] = src[d];
+      }
+      if (P.logw_out) P.logw_out[(size_t)n * P.M_out + j] = soft ? diff[idx] : uniform_lw;
+    }
+  }
+}
+
+static size_t resample_smem_bytes(int M, bool soft) {
+  const int Mpad = ((M + GROUP - 1) / GROUP) * GROUP;
+  size_t floats = 32 + (size_t)Mpad + Mpad / SEG + Mpad / GROUP + 4 + (soft ? M : 0);
+  return floats * sizeof(float);
+}
+
+int launch_normalize_resample(const ResampleParams& P, cudaStream_t stream) {
+  const bool soft = P.alpha < 1.0f;
+  const size_t smem = resample_smem_bytes(P.M, soft);
+  if (smem > 227 * 1024) {
+    set_error("normalize_resample: M=%d needs %zu B of shared memory; the large-M path is not built yet", P.M, smem);
+    return MMF_E_UNSUPPORTED;
+  }
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  MMF_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    MMF_CUDA(cudaFuncSetAttribute(k_normalize_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured_dev = dev;
+  }
+  int sms = 148;
+  MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // enough CTAs per SM to hide the serial CDF chain of one trajectory behind the others
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  long long grid = (long long)sms * per_sm;
+  if (grid > P.N) grid = P.N;
+  k_normalize_resample<<<(int)grid, NR_TPB, smem, stream>>>(P);
+  MMF_LAUNCH_CHECK("k_normalize_resample");
+  return MMF_OK;
+}
+
+// ---- mmf_fuse_loglik: (N,M,K) x (N,K) -> (N,M), torch.logsumexp semantics ------------------------
+__global__ void k_fuse_loglik(int N, int M, int K, const float* __restrict__ ll, const float* __restrict__ w,
+                              float* __restrict__ out) {
+  const long long total = (long long)N * M;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(p / M);
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, ll[p * K + k] + (w ? w[(size_t)n * K + k] : 0.0f));
+    const float shift = (mx == -INFINITY || mx == INFINITY) ? 0.0f : mx;
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s += expf(ll[p * K + k] + (w ? w[(size_t)n * K + k] : 0.0f) - shift);
+    out[p] = shift + logf(s);
+  }
+}
+
+int launch_fuse_loglik(int N, int M, int K, const float* ll, const float* w, float* out, cudaStream_t stream) {
+  const long long total = (long long)N * M;
+  if (total == 0) return MMF_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_fuse_loglik<<<(int)blocks, 256, 0, stream>>>(N, M, K, ll, w, out);
+  MMF_LAUNCH_CHECK("k_fuse_loglik");
+  return MMF_OK;
+}
+
+// ---- mmf_pf_init (R2) ------------------------------------------------------------------------------------
+__global__ void k_pf_init(int N, int M, int sd, const float* __restrict__ mean, const float* __restrict__ cov,
+                          const float* __restrict__ eps, float* __restrict__ states, float* __restrict__ logw) {
+  const long long total = (long long)N * M;
+  const float lw = -logf((float)M);
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(p / M), m = (int)(p % M);
+    // Cholesky of the small sd x sd covariance (lower factor), recomputed per thread (sd <= 4)
+    float L[MMF_MAX_SD][MMF_MAX_SD];
+    const float* C = cov + (size_t)n * sd * sd;
+    for (int i = 0; i < sd; ++i) {
+      for (int j = 0; j <= i; ++j) {
+        float s = C[i * sd + j];
+        for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+        L[i][j] = (i == j) ? sqrtf(s) : s / L[j][j];
+      }
+    }
+    const float* e = eps + ((size_t)m * N + n) * sd;
+    for (int i = 0; i < sd; ++i) {
+      float v = 0.0f;
+      for (int j = 0; j <= i; ++j) v = fmaf(L[i][j], e[j], v);
+      states[p * sd + i] = mean[(size_t)n * sd + i] + v;
+    }
+    logw[p] = lw;
+  }
+}
+
+int launch_pf_init(int N, int M, int sd, const float* mean, const float* cov, const float* eps, float* states,
+                   float* logw, cudaStream_t stream) {
+  const long long total = (long long)N * M;
+  if (total == 0) return MMF_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_pf_init<<<(int)blocks, 256, 0, stream>>>(N, M, sd, mean, cov, eps, states, logw);
+  MMF_LAUNCH_CHECK("k_pf_init");
+  return MMF_OK;
+}
+
+}  // namespace mmf

@@ -1,0 +1,226 @@
+"""Tensor-level wrappers over the C ABI (``_lib``): shape checks, output allocation, pointer
+marshalling.  Every function here launches hand-written sm_100a kernels; none has a torch or CPU
+fallback."""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (  # noqa: F401  (re-exported constants)
+    ESTIMATE_ARGMAX,
+    ESTIMATE_WEIGHTED_AVERAGE,
+    PREC_BF16,
+    PREC_BF16X3,
+    PREC_FP32,
+    RESAMPLE_MULTINOMIAL_FAST,
+    RESAMPLE_MULTINOMIAL_STRICT,
+    RESAMPLE_NONE,
+    RESAMPLE_SYSTEMATIC_FAST,
+    RESAMPLE_SYSTEMATIC_STRICT,
+)
+
+RESAMPLE_MODES = {
+    "multinomial": RESAMPLE_MULTINOMIAL_STRICT,
+    "multinomial_fast": RESAMPLE_MULTINOMIAL_FAST,
+    "systematic": RESAMPLE_SYSTEMATIC_STRICT,
+    "systematic_fast": RESAMPLE_SYSTEMATIC_FAST,
+}
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+ESTIMATION = {"weighted_average": ESTIMATE_WEIGHTED_AVERAGE, "argmax": ESTIMATE_ARGMAX}
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise _lib.MMFError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def is_systematic(mode: int) -> bool:
+    return mode in (RESAMPLE_SYSTEMATIC_STRICT, RESAMPLE_SYSTEMATIC_FAST)
+
+
+def pf_init(mean, covariance, eps_MNsd):
+    """R2: (N,sd), (N,sd,sd), (M,N,sd) -> particle_states (N,M,sd), particle_log_weights (N,M)."""
+    lib = _lib.load()
+    M, N, sd = eps_MNsd.shape
+    assert mean.shape == (N, sd) and covariance.shape == (N, sd, sd)
+    mean, covariance, eps_MNsd = _f32c(mean), _f32c(covariance), _f32c(eps_MNsd)
+    states = torch.empty((N, M, sd), device=mean.device, dtype=torch.float32)
+    logw = torch.empty((N, M), device=mean.device, dtype=torch.float32)
+    _lib.check(
+        lib.mmf_pf_init(N, M, sd, _lib.ptr(mean), _lib.ptr(covariance), _lib.ptr(eps_MNsd), _lib.ptr(states),
+                        _lib.ptr(logw), _lib.stream_of(mean))
+    )
+    return states, logw
+
+
+def pf_traj_rows(model_struct, K, controls, obs_feats):
+    """Hoisted per-trajectory rows: controls (N,cd), obs_feats list of K tensors (N,F_k) or None."""
+    lib = _lib.load()
+    controls = _f32c(controls)
+    N = controls.shape[0]
+    feats = [None if f is None else _f32c(f) for f in obs_feats]
+    arr = (C.c_void_p * _lib.MAX_HEADS)()
+    for k in range(K):
+        arr[k] = None if feats[k] is None else feats[k].data_ptr()
+    out = torch.empty((1 + K, N, _lib.UNITS), device=controls.device, dtype=torch.float32)
+    _lib.check(
+        lib.mmf_pf_traj_rows(C.byref(model_struct), N, _lib.ptr(controls), arr, _lib.ptr(out), _lib.stream_of(controls))
+    )
+    return out
+
+
+def pf_predict_measure(model_struct, states, eps, rowbias, logw, modality_logw, enabled_mask, precision=PREC_FP32,
+                       want_ll=False):
+    """R3+R4+R5: states (N,M,sd), eps (N*M,sd), rowbias (1+K,N,64), logw (N,M), modality_logw (N,K)|None
+    -> states_new (N,M,sd), logw_unnorm (N,M) [, ll (K,N,M)]."""
+    lib = _lib.load()
+    N, M, sd = states.shape
+    states, eps, rowbias, logw = _f32c(states), _f32c(eps), _f32c(rowbias), _f32c(logw)
+    assert eps.numel() == N * M * sd and logw.shape == (N, M)
+    K = model_struct.num_heads
+    if modality_logw is not None:
+        modality_logw = _f32c(modality_logw)
+        assert modality_logw.shape == (N, K), (modality_logw.shape, (N, K))
+    states_out = torch.empty_like(states)
+    logw_out = torch.empty_like(logw)
+    ll = torch.full((K, N, M), float("nan"), device=states.device, dtype=torch.float32) if want_ll else None
+    _lib.check(
+        lib.mmf_pf_predict_measure(
+            C.byref(model_struct), N, M, _lib.ptr(states), _lib.ptr(eps), _lib.ptr(rowbias), _lib.ptr(logw),
+            _lib.ptr(modality_logw), enabled_mask, precision, _lib.ptr(states_out), _lib.ptr(logw_out),
+            _lib.ptr(ll), _lib.stream_of(states),
+        )
+    )
+    return (states_out, logw_out, ll) if want_ll else (states_out, logw_out)
+
+
+def pf_normalize_resample(states, logw_unnorm, *, estimation=ESTIMATE_WEIGHTED_AVERAGE, mode=RESAMPLE_NONE,
+                          alpha=1.0, M_out=None, uniforms=None, want_debug=False):
+    """Second half of R6 + R7.  Returns dict(states, logw, estimate[, logw_norm, logits, idx])."""
+    lib = _lib.load()
+    N, M, sd = states.shape
+    states, logw_unnorm = _f32c(states), _f32c(logw_unnorm)
+    assert logw_unnorm.shape == (N, M)
+    dev = states.device
+    est = torch.empty((N, sd), device=dev, dtype=torch.float32)
+    resample = mode != RESAMPLE_NONE
+    if resample:
+        M_out = M if M_out is None else M_out
+        assert uniforms is not None and uniforms.dtype == torch.float64
+        uniforms = uniforms.contiguous()
+        assert uniforms.shape == ((N,) if is_systematic(mode) else (N, M_out)), uniforms.shape
+        states_out = torch.empty((N, M_out, sd), device=dev, dtype=torch.float32)
+        logw_out = torch.empty((N, M_out), device=dev, dtype=torch.float32)
+    else:
+        M_out = M
+        states_out = None
+        logw_out = torch.empty((N, M), device=dev, dtype=torch.float32)
+    logw_norm = torch.empty((N, M), device=dev, dtype=torch.float32) if want_debug else None
+    logits = torch.empty((N, M), device=dev, dtype=torch.float32) if (want_debug and resample) else None
+    idx = torch.empty((N, M_out), device=dev, dtype=torch.int64) if (want_debug and resample) else None
+    _lib.check(
+        lib.mmf_pf_normalize_resample(
+            N, M, sd, _lib.ptr(states), _lib.ptr(logw_unnorm), estimation, mode, float(alpha), M_out,
+            _lib.ptr(uniforms), _lib.ptr(states_out), _lib.ptr(logw_out), _lib.ptr(est), _lib.ptr(logw_norm),
+            _lib.ptr(logits), _lib.ptr(idx), None, _lib.stream_of(states),
+        )
+    )
+    out = {"states": states_out if resample else states, "logw": logw_out, "estimate": est}
+    if want_debug:
+        out.update(logw_norm=logw_norm, logits=logits, idx=idx)
+    return out
+
+
+def fuse_loglik(ll, w=None):
+    """R5 standalone: ll (N,M,K), w (N,K)|None -> (N,M)."""
+    lib = _lib.load()
+    N, M, K = ll.shape
+    ll = _f32c(ll)
+    w = None if w is None else _f32c(w)
+    out = torch.empty((N, M), device=ll.device, dtype=torch.float32)
+    _lib.check(lib.mmf_fuse_loglik(N, M, K, _lib.ptr(ll), _lib.ptr(w), _lib.ptr(out), _lib.stream_of(ll)))
+    return out
+
+
+def resample_indices(logits, uniforms, mode=RESAMPLE_MULTINOMIAL_STRICT, M_out=None):
+    """R7 standalone: logits (N,M), float64 uniforms -> int64 (N,M_out)."""
+    lib = _lib.load()
+    N, M = logits.shape
+    logits = _f32c(logits)
+    assert uniforms.dtype == torch.float64
+    uniforms = uniforms.contiguous()
+    if M_out is None:
+        M_out = M if is_systematic(mode) else uniforms.shape[1]
+    idx = torch.empty((N, M_out), device=logits.device, dtype=torch.int64)
+    _lib.check(
+        lib.mmf_resample(N, M, M_out, _lib.ptr(logits), mode, _lib.ptr(uniforms), _lib.ptr(idx), None,
+                         _lib.stream_of(logits))
+    )
+    return idx
+
+
+def ekf_loop(model_structs, mean0, cov0, controls, z, r_tril):
+    """R8 for F filters x T steps: mean0 (F,N,sd), cov0 (F,N,sd,sd), controls (T,N,cd), z (F,T,N,sd),
+    r_tril (F,T,N,sd,sd) -> means (F,T,N,sd), covs (F,T,N,sd,sd)."""
+    lib = _lib.load()
+    F = len(model_structs)
+    arr = (_lib.EKFModel * F)(*model_structs)
+    mean0, cov0, controls, z, r_tril = map(_f32c, (mean0, cov0, controls, z, r_tril))
+    _, T, N, sd = z.shape
+    assert mean0.shape == (F, N, sd) and cov0.shape == (F, N, sd, sd)
+    assert controls.shape[:2] == (T, N) and r_tril.shape == (F, T, N, sd, sd)
+    means = torch.empty((F, T, N, sd), device=z.device, dtype=torch.float32)
+    covs = torch.empty((F, T, N, sd, sd), device=z.device, dtype=torch.float32)
+    _lib.check(
+        lib.mmf_ekf_loop_fwd(arr, F, T, N, _lib.ptr(mean0), _lib.ptr(cov0), _lib.ptr(controls), _lib.ptr(z),
+                             _lib.ptr(r_tril), _lib.ptr(means), _lib.ptr(covs), _lib.stream_of(z))
+    )
+    return means, covs
+
+
+def dynamics_jacobian(model_struct, states, controls):
+    """A.4: states (N,sd), controls (N,cd) -> pred (N,sd), jacobian (N,sd,sd)."""
+    lib = _lib.load()
+    states, controls = _f32c(states), _f32c(controls)
+    N, sd = states.shape
+    pred = torch.empty_like(states)
+    jac = torch.empty((N, sd, sd), device=states.device, dtype=torch.float32)
+    _lib.check(
+        lib.mmf_dynamics_jacobian(C.byref(model_struct), N, _lib.ptr(states), _lib.ptr(controls), _lib.ptr(pred),
+                                  _lib.ptr(jac), _lib.stream_of(states))
+    )
+    return pred, jac
+
+
+def kf_fuse_crossmodal(mu, P, beta):
+    """R10: mu (K,*,sd), P (K,*,sd,sd), beta (K,*,sd) -> mean (*,sd), cov (*,sd,sd)."""
+    lib = _lib.load()
+    K, sd = mu.shape[0], mu.shape[-1]
+    lead = mu.shape[1:-1]
+    rows = int(math.prod(lead))
+    mu, P, beta = _f32c(mu), _f32c(P), _f32c(beta)
+    mean = torch.empty((*lead, sd), device=mu.device, dtype=torch.float32)
+    cov = torch.empty((*lead, sd, sd), device=mu.device, dtype=torch.float32)
+    _lib.check(
+        lib.mmf_kf_fuse_crossmodal(K, rows, sd, _lib.ptr(mu), _lib.ptr(P), _lib.ptr(beta), _lib.ptr(mean),
+                                   _lib.ptr(cov), _lib.stream_of(mu))
+    )
+    return mean, cov
+
+
+def kf_fuse_unimodal(mu, P):
+    """R11: information-form fusion of K Gaussian posteriors."""
+    lib = _lib.load()
+    K, sd = mu.shape[0], mu.shape[-1]
+    lead = mu.shape[1:-1]
+    rows = int(math.prod(lead))
+    mu, P = _f32c(mu), _f32c(P)
+    mean = torch.empty((*lead, sd), device=mu.device, dtype=torch.float32)
+    cov = torch.empty((*lead, sd, sd), device=mu.device, dtype=torch.float32)
+    _lib.check(
+        lib.mmf_kf_fuse_unimodal(K, rows, sd, _lib.ptr(mu), _lib.ptr(P), _lib.ptr(mean), _lib.ptr(cov),
+                                 _lib.stream_of(mu))
+    )
+    return mean, cov

@@ -1,0 +1,365 @@
+"""``ParticleFilter`` / ``ExtendedKalmanFilter`` / ``VirtualSensorExtendedKalmanFilter`` with
+torchfilter's public surface (reference call sites
+ref: crossmodal/push_models/pf.py:14-27, crossmodal/door_models/kf.py:14-28,
+crossmodal/eval_helpers.py:125-142), executing in the sm_100a kernels of ``libmmf_b200.so``.
+
+Dispatch:
+  * recognised architectures (the reference's gated-residual dynamics and per-particle heads,
+    see ``fused.py``) and no autograd  -> fully fused kernels, observation encoders hoisted over T;
+  * anything else (user-defined modules, or gradients required) -> the modules run as torch
+    modules on the GPU and only the reweight / normalise / estimate / resample stages run in the
+    kernels (torch ops where a gradient has to flow).
+Extensions beyond upstream (all optional, defaults reproduce upstream behaviour):
+  ``noise``          object supplying the random draws (``init_eps``, ``process_eps``,
+                     ``resample_uniforms``) so that two implementations can be fed identical draws;
+  ``resample_mode``  "multinomial" (upstream's inverse-CDF, torch.multinomial's CPU arithmetic),
+                     "multinomial_fast", "systematic", "systematic_fast";
+  ``precision``      "fp32" | "bf16x3" | "bf16" arithmetic of the per-particle MLP chain.
+"""
+import math
+
+import torch
+
+from .. import _lib, fused, ops
+from ..fannypack.utils import SliceWrapper
+from .base import (
+    DynamicsModel,
+    Filter,
+    KalmanFilterBase,
+    KalmanFilterMeasurementModel,
+    ParticleFilterMeasurementModel,
+    VirtualSensorModel,
+    require_cuda,
+)
+
+TIME_BATCHABLE = {
+    # per-trajectory modules whose rows are independent, so (T, N, ...) can be run as one (T*N) batch
+    "PushCrossmodalWeightModel", "DoorCrossmodalWeightModel", "PushVirtualSensorModel", "DoorVirtualSensorModel",
+}
+
+
+def _needs_grad(module, *tensors) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def _has_hooks(module) -> bool:
+    return bool(module._forward_hooks or module._forward_pre_hooks)
+
+
+class ParticleFilter(Filter):
+    def __init__(
+        self,
+        *,
+        dynamics_model: DynamicsModel,
+        measurement_model: ParticleFilterMeasurementModel,
+        num_particles: int = 100,
+        resample=None,
+        soft_resample_alpha: float = 1.0,
+        estimation_method: str = "weighted_average",
+    ):
+        super().__init__(state_dim=dynamics_model.state_dim)
+        assert isinstance(dynamics_model, DynamicsModel)
+        assert isinstance(measurement_model, ParticleFilterMeasurementModel)
+        self.dynamics_model = dynamics_model
+        self.measurement_model = measurement_model
+        self.num_particles = num_particles
+        self.resample = resample
+        self.soft_resample_alpha = soft_resample_alpha
+        self.estimation_method = estimation_method
+        self.particle_states = None
+        self.particle_log_weights = None
+        self._initialized = False
+        # extensions
+        self.noise = None
+        self.resample_mode = "multinomial"
+        self.precision = "fp32"
+        self.debug = None  # set to a dict to capture intermediates of the last fused step
+
+    # ---- plan management -------------------------------------------------------------------------
+    def fused_plan(self):
+        key = (id(self.dynamics_model), id(self.measurement_model))
+        cached = self.__dict__.get("_mmf_plan")
+        if cached is None or cached[0] != key:
+            cached = (key, fused.PFPlan.build(self))
+            self.__dict__["_mmf_plan"] = cached
+        return cached[1]
+
+    # ---- random draws ------------------------------------------------------------------------------
+    def _init_eps(self, M, N, sd, like):
+        if self.noise is not None:
+            return self.noise.init_eps(M, N, sd, like).to(like.device, torch.float32)
+        return torch.randn((M, N, sd), device=like.device, dtype=torch.float32)
+
+    def _process_eps(self, rows, sd, like):
+        if self.noise is not None:
+            return self.noise.process_eps(rows, sd, like).to(like.device, torch.float32)
+        return torch.randn((rows, sd), device=like.device, dtype=torch.float32)
+
+    def _uniforms(self, N, S, like, mode):
+        if self.noise is not None:
+            u = self.noise.resample_uniforms(N, S, like)
+            return u.to(like.device, torch.float64)
+        if ops.is_systematic(mode):
+            return torch.rand((N,), device=like.device, dtype=torch.float64)
+        return torch.rand((N * S,), device=like.device, dtype=torch.float64).reshape(N, S)
+
+    # ---- A.3 initialize_beliefs (R2) ------------------------------------------------------------------
+    def initialize_beliefs(self, *, mean: torch.Tensor, covariance: torch.Tensor) -> None:
+        N = mean.shape[0]
+        sd, M = self.state_dim, self.num_particles
+        assert mean.shape == (N, sd)
+        assert covariance.shape == (N, sd, sd)
+        require_cuda(mean, "initialize_beliefs(mean=...)")
+        eps = self._init_eps(M, N, sd, mean)
+        self.particle_states, self.particle_log_weights = ops.pf_init(
+            mean.detach().float(), covariance.detach().float().contiguous(), eps
+        )
+        self._initialized = True
+
+    # ---- one step ----------------------------------------------------------------------------------------
+    def _modes(self):
+        resample = self.resample if self.resample is not None else (not self.training)
+        mode = ops.RESAMPLE_MODES[self.resample_mode] if resample else ops.RESAMPLE_NONE
+        assert self.estimation_method in ops.ESTIMATION, f"unknown estimation method {self.estimation_method}"
+        return resample, mode
+
+    def _retile_without_resampling(self):
+        """A.3: particle count changed while resampling is off -> tile, pad with a random subset."""
+        N, M, sd = self.particle_states.shape
+        reps, extra = divmod(self.num_particles, M)
+        idx = torch.arange(M, device=self.particle_states.device).repeat(reps)
+        if extra:
+            perm = self.noise.randperm(M) if self.noise is not None else torch.randperm(M)
+            idx = torch.cat([idx, perm[:extra].to(idx.device)])
+        self.particle_states = self.particle_states[:, idx, :].contiguous()
+        logw = self.particle_log_weights[:, idx]
+        self.particle_log_weights = (logw - torch.logsumexp(logw, dim=1, keepdim=True)).contiguous()
+
+    def forward(self, *, observations, controls, _hoisted=None) -> torch.Tensor:
+        assert self._initialized, "Particle filter not initialized: call initialize_beliefs() first"
+        require_cuda(self.particle_states, "the particle set")
+        resample, mode = self._modes()
+        if not resample and self.num_particles != self.particle_states.shape[1]:
+            self._retile_without_resampling()
+        plan = self.fused_plan()
+        grad = _needs_grad(self, self.particle_states, self.particle_log_weights)
+        if plan is not None and not grad and isinstance(controls, torch.Tensor):
+            return self._step_fused(plan, observations, controls, mode, _hoisted)
+        return self._step_generic(observations, controls, resample, mode, grad)
+
+    def _step_fused(self, plan, observations, controls, mode, hoisted):
+        states, logw = self.particle_states, self.particle_log_weights
+        N, M, sd = states.shape
+        with torch.no_grad():
+            if hoisted is None:
+                feats = plan.head_features(observations)
+                modw = plan.modality_log_weights(observations)
+            else:
+                feats, modw = hoisted
+            eps = self._process_eps(N * M, sd, states)
+            uniforms = self._uniforms(N, self.num_particles, states, mode) if mode != ops.RESAMPLE_NONE else None
+            out = plan.step(
+                states, logw, controls, feats, modw, eps,
+                precision=ops.PRECISIONS[self.precision], estimation=ops.ESTIMATION[self.estimation_method],
+                mode=mode, alpha=self.soft_resample_alpha, M_out=self.num_particles, uniforms=uniforms,
+                want_debug=self.debug is not None,
+            )
+        self.particle_states, self.particle_log_weights = out["states"], out["logw"]
+        if self.debug is not None:
+            self.debug.clear()
+            self.debug.update(out, eps=eps, uniforms=uniforms)
+        return out["estimate"]
+
+    def _step_generic(self, observations, controls, resample, mode, grad):
+        states, logw = self.particle_states, self.particle_log_weights
+        N, M, sd = states.shape
+        flat_controls = SliceWrapper(controls).map(lambda c: c.repeat_interleave(M, dim=0))
+        pred, trils = self.dynamics_model(initial_states=states.reshape(-1, sd), controls=flat_controls)
+        eps = self._process_eps(N * M, sd, states)
+        moved = (pred + (trils @ eps[..., None]).squeeze(-1)).view(N, M, sd)
+        logw_unnorm = logw + self.measurement_model(states=moved, observations=observations)
+        assert logw_unnorm.shape == (N, M)
+        uniforms = self._uniforms(N, self.num_particles, states, mode) if resample else None
+        if not grad:
+            out = ops.pf_normalize_resample(
+                moved.detach(), logw_unnorm.detach(), estimation=ops.ESTIMATION[self.estimation_method], mode=mode,
+                alpha=self.soft_resample_alpha, M_out=self.num_particles, uniforms=uniforms,
+            )
+            self.particle_states, self.particle_log_weights = out["states"], out["logw"]
+            return out["estimate"]
+        # gradient path: differentiable torch ops; only the (non-differentiable) index draw is a kernel
+        logw_n = logw_unnorm - torch.logsumexp(logw_unnorm, dim=1, keepdim=True)
+        if self.estimation_method == "weighted_average":
+            estimate = torch.sum(torch.exp(logw_n)[:, :, None] * moved, dim=1)
+        else:
+            best = torch.argmax(logw_n, dim=1)
+            estimate = moved[torch.arange(N, device=best.device), best]
+        if resample:
+            alpha = self.soft_resample_alpha
+            uniform_lw = logw_n.new_full((N, self.num_particles), -math.log(M))
+            if alpha < 1.0:
+                assert self.num_particles == M
+                logits = torch.logsumexp(
+                    torch.stack([logw_n + math.log(alpha), uniform_lw + math.log(1.0 - alpha)]), dim=0
+                )
+                new_logw = logw_n - logits
+            else:
+                logits, new_logw = logw_n, uniform_lw
+            idx = ops.resample_indices(logits.detach().contiguous(), uniforms, mode=mode, M_out=self.num_particles)
+            moved = torch.gather(moved, 1, idx[:, :, None].expand(N, self.num_particles, sd))
+            logw_n = torch.gather(new_logw, 1, idx) if alpha < 1.0 else new_logw
+        self.particle_states, self.particle_log_weights = moved, logw_n
+        return estimate
+
+    # ---- whole sequence (R1) -----------------------------------------------------------------------------
+    def forward_loop(self, *, observations, controls) -> torch.Tensor:
+        plan = self.fused_plan()
+        if (
+            plan is None
+            or not self._initialized
+            or not isinstance(controls, torch.Tensor)
+            or not isinstance(observations, dict)
+            or _has_hooks(self)
+            or _needs_grad(self, self.particle_states, self.particle_log_weights)
+        ):
+            return super().forward_loop(observations=observations, controls=controls)
+        require_cuda(controls, "controls")
+        T, N = controls.shape[:2]
+        assert SliceWrapper(observations).shape[:2] == (T, N), "observations and controls disagree on (T, N)"
+        feats, modw = self.hoist_observations(plan, observations, T, N)
+        estimates = controls.new_zeros((T, N, self.state_dim), dtype=torch.float32)
+        for t in range(T):
+            hoisted = ([None if f is None else f[t] for f in feats], None if modw is None else modw[t])
+            estimates[t] = self.forward(observations=None, controls=controls[t], _hoisted=hoisted)
+        return estimates
+
+    def hoist_observations(self, plan, observations, T, N):
+        """The observation encoders and the weight model do not depend on the particles: run them
+        once over all T*N rows instead of once per step per model."""
+        with torch.no_grad():
+            enabled = plan.enabled()
+            feats = []
+            for h, on in zip(plan.heads, enabled):
+                if not on:
+                    feats.append(None)
+                    continue
+                chunks = fused.batched_over_time(h.observation_features, observations, T, N)
+                feats.append(torch.cat(chunks).reshape(T, N, -1).contiguous())
+            wm = getattr(plan.mm, "crossmodal_weight_model", None) if plan.composite else None
+            if wm is None:
+                modw = None
+            elif type(wm).__name__ in TIME_BATCHABLE or getattr(wm, "_mmf_time_batchable", False):
+                chunks = fused.batched_over_time(lambda o: wm(observations=o), observations, T, N)
+                modw = torch.cat(chunks).reshape(T, N, -1).contiguous()
+            else:
+                obs = SliceWrapper(observations)
+                modw = torch.stack([wm(observations=obs[t]) for t in range(T)]).contiguous()
+        return feats, modw
+
+
+class ExtendedKalmanFilter(KalmanFilterBase):
+    """A.5 for arbitrary user models (torch ops on the GPU).  The fused kernel path lives in
+    ``VirtualSensorExtendedKalmanFilter``, the only EKF flavour the reference instantiates."""
+
+    def _predict_step(self, *, controls):
+        mean, cov = self._belief_mean, self._belief_covariance
+        pred, q_tril = self.dynamics_model(initial_states=mean, controls=controls)
+        A = self.dynamics_model.jacobian(initial_states=mean, controls=controls)
+        self._belief_mean = pred
+        self._belief_covariance = A @ cov @ A.transpose(-1, -2) + q_tril @ q_tril.transpose(-1, -2)
+
+    def _update_step(self, *, observations):
+        mean, cov = self._belief_mean, self._belief_covariance
+        expected, r_tril = self.measurement_model(states=mean)
+        Cm = self.measurement_model.jacobian(states=mean)
+        S = Cm @ cov @ Cm.transpose(-1, -2) + r_tril @ r_tril.transpose(-1, -2)
+        gain = cov @ Cm.transpose(-1, -2) @ torch.inverse(S)
+        self._belief_mean = mean + (gain @ (observations - expected)[:, :, None]).squeeze(-1)
+        eye = torch.eye(self.state_dim, device=cov.device, dtype=cov.dtype)
+        self._belief_covariance = (eye - gain @ Cm) @ cov
+
+
+class _IdentityMeasurementModel(KalmanFilterMeasurementModel):
+    def __init__(self, *, state_dim: int):
+        super().__init__(state_dim=state_dim, observation_dim=state_dim)
+        self.scale_tril = None
+
+    def forward(self, *, states):
+        assert self.scale_tril is not None
+        return states, self.scale_tril
+
+    def jacobian(self, *, states):
+        eye = torch.eye(self.state_dim, device=states.device, dtype=states.dtype)
+        return eye[None].expand(states.shape[0], self.state_dim, self.state_dim)
+
+
+class VirtualSensorExtendedKalmanFilter(ExtendedKalmanFilter):
+    def __init__(self, *, dynamics_model: DynamicsModel, virtual_sensor_model: VirtualSensorModel):
+        super().__init__(
+            dynamics_model=dynamics_model,
+            measurement_model=_IdentityMeasurementModel(state_dim=dynamics_model.state_dim),
+        )
+        self.virtual_sensor_model = virtual_sensor_model
+
+    def fused_plan(self):
+        key = id(self.dynamics_model)
+        cached = self.__dict__.get("_mmf_plan")
+        if cached is None or cached[0] != key:
+            cached = (key, fused.EKFPlan.build([self]))
+            self.__dict__["_mmf_plan"] = cached
+        return cached[1]
+
+    def _use_fused(self, controls):
+        return (
+            isinstance(controls, torch.Tensor)
+            and self.fused_plan() is not None
+            and not _needs_grad(self, self._belief_mean, self._belief_covariance)
+        )
+
+    def forward(self, *, observations, controls):
+        assert self._initialized, "Kalman filter not initialized: call initialize_beliefs() first"
+        require_cuda(self._belief_mean, "the belief mean")
+        z, r_tril = self.virtual_sensor_model(observations=observations)
+        if not self._use_fused(controls):
+            self.measurement_model.scale_tril = r_tril
+            return super().forward(observations=z, controls=controls)
+        assert controls.shape[0] == self._belief_mean.shape[0]
+        means, covs = self.fused_plan().loop(
+            self._belief_mean.detach()[None], self._belief_covariance.detach()[None].contiguous(),
+            controls[None], z.detach()[None, None], r_tril.detach()[None, None],
+        )
+        self._belief_mean, self._belief_covariance = means[0, 0], covs[0, 0]
+        return self._belief_mean
+
+    def sense_sequence(self, observations, T, N):
+        """Virtual-sensor outputs for all T steps: z (T,N,sd), r_tril (T,N,sd,sd)."""
+        vs = self.virtual_sensor_model
+        with torch.no_grad():
+            if type(vs).__name__ in TIME_BATCHABLE or getattr(vs, "_mmf_time_batchable", False):
+                outs = fused.batched_over_time(lambda o: vs(observations=o), observations, T, N)
+                z = torch.cat([o[0] for o in outs]).reshape(T, N, -1)
+                r = torch.cat([o[1] for o in outs]).reshape(T, N, self.state_dim, self.state_dim)
+            else:
+                obs = SliceWrapper(observations)
+                outs = [vs(observations=obs[t]) for t in range(T)]
+                z = torch.stack([o[0] for o in outs])
+                r = torch.stack([o[1] for o in outs])
+        return z.contiguous(), r.contiguous()
+
+    def forward_loop(self, *, observations, controls):
+        if not self._initialized or not self._use_fused(controls) or _has_hooks(self) or not isinstance(observations, dict):
+            return super().forward_loop(observations=observations, controls=controls)
+        require_cuda(controls, "controls")
+        T, N = controls.shape[:2]
+        assert SliceWrapper(observations).shape[:2] == (T, N), "observations and controls disagree on (T, N)"
+        z, r_tril = self.sense_sequence(observations, T, N)
+        means, covs = self.fused_plan().loop(
+            self._belief_mean.detach()[None], self._belief_covariance.detach()[None].contiguous(),
+            controls, z[None], r_tril[None],
+        )
+        self._belief_mean, self._belief_covariance = means[0, -1], covs[0, -1]
+        return means[0]

@@ -27,7 +27,7 @@ class TorchRNGNoise:
     def resample_uniforms(self, N, S):
         return torch.rand(N * S, dtype=torch.float64).reshape(N, S)
 
-    def resample_indices(self, probs, S):
+    def resample_indices(self, probs, S, logits=None):
         return multinomial_inverse_cdf(probs, self.resample_uniforms(probs.shape[0], S))
 
     def randperm(self, M):
@@ -41,12 +41,16 @@ class RecordedNoise:
     positions (u0 + j) / S, the north-star low-variance variant that upstream does not have).
     """
 
-    def __init__(self, *, init_eps=None, process_eps=(), uniforms=(), mode="multinomial"):
+    def __init__(self, *, init_eps=None, process_eps=(), uniforms=(), mode="multinomial", arithmetic="torch"):
         self._init = init_eps
         self._eps = list(process_eps)
         self._u = list(uniforms)
-        self.mode = mode
+        self.mode = mode  # multinomial | multinomial_fast | systematic | systematic_fast
+        # "torch": torch's softmax + sequential fp32 CDF (what torch.multinomial does on CPU);
+        # "pinned": the fully specified arithmetic of oracle/pinned/mmf_pinned.c (required for *_fast)
+        self.arithmetic = arithmetic
         self.probs_seen = []
+        self.indices = []
 
     def init_eps(self, M, N, sd, like):
         assert self._init.shape == (M, N, sd)
@@ -57,15 +61,25 @@ class RecordedNoise:
         assert eps.shape == (rows, sd)
         return eps.to(like.dtype)
 
-    def resample_indices(self, probs, S):
+    def resample_indices(self, probs, S, logits=None):
         u = self._u.pop(0)
         self.probs_seen.append(probs.detach().clone())
+        if self.arithmetic == "pinned":
+            from oracle import pinned
+
+            idx = pinned.resample(logits.detach().cpu().numpy(), u.cpu().numpy(), self.mode, num_samples=S)
+            idx = torch.from_numpy(idx)
+            self.indices.append(idx)
+            return idx
+        assert self.mode in ("multinomial", "systematic"), "the blocked summation order only exists pinned"
         if self.mode == "systematic":
             assert u.shape == (probs.shape[0],)
             j = torch.arange(S, dtype=torch.float64)
             u = (u.double()[:, None] + j[None, :]) / float(S)
         assert u.shape == (probs.shape[0], S)
-        return multinomial_inverse_cdf(probs, u)
+        idx = multinomial_inverse_cdf(probs, u)
+        self.indices.append(idx)
+        return idx
 
     def randperm(self, M):
         return torch.randperm(M)

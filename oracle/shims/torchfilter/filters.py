@@ -162,7 +162,7 @@ class ParticleFilter(Filter):
         else:
             normalised = logits - torch.logsumexp(logits, dim=-1, keepdim=True)
             probs = torch.softmax(normalised, dim=-1)
-            idx = self.noise.resample_indices(probs, Mout)
+            idx = self.noise.resample_indices(probs, Mout, logits=logits)
         assert idx.shape == (N, Mout)
 
         self.particle_states = torch.gather(
