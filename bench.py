@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/sec of the filtering recursion on B200 (contract: task statement section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c2] [--impl b200|reference]
+
+A "step" is ONE pass of the hot path over one batch of synthetic trajectories: the whole
+``forward_loop`` of the named BASELINE config (T filter steps for N trajectories).
+
+  value  particle-steps/s of the recursion with its inputs (hoisted observation features, controls)
+         resident in HBM; noise is drawn on the device inside the timed region, as torchfilter does.
+  e2e    the same metric through the public API ``filter.forward_loop(observations=, controls=)``
+         with PINNED HOST buffers: H2D of the raw observations (images included), the observation
+         encoders, the recursion, and the D2H read of the estimates are all inside the timed region.
+  roofline      the dominant kernel (the per-particle MLP chain) timed live with CUDA events on its
+                stream: algorithmic FLOPs (189,824 / particle-step, hoisted
+                minimum) / launch time vs the measured bf16 peak of MEASURED_PEAKS.json.
+  cpu_baseline  the oracle port (eager PyTorch, CPU, all host threads) on a bounded sample.
+
+Multi-GPU: trajectories are sharded, N per rank is fixed (weak scaling), no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (model class, state_dim, N per GPU, particles, T, BASELINE.json config string)
+    "c3": ("PushUnimodalParticleFilter", 2, 4096, 1000, 100,
+           "Push task unimodal weighted-fusion PF, 4096 trajectories x 1000 particles x 100 steps"),
+    "c1": ("PushCrossmodalParticleFilter", 2, 32, 30, 50,
+           "Push task crossmodal PF eval (state_dim=2, 30 particles), 32 trajectories x 50 steps"),
+    "c2": ("DoorCrossmodalKalmanFilter", 3, 256, 1, 100,
+           "Door task crossmodal EKF eval (state_dim=3), 256 trajectories x 100 steps"),
+}
+FLOP_PER_PARTICLE_STEP = {2: 189_824.0, 3: 190_336.0}  # BASELINE.md section 4 (hoisted minimum)
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) == 6 and parts[0].isdigit():
+                self.samples.append(parts)
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def build_inputs(workload, seed=0):
+    from multimodalfilter_b200.synthetic import synthetic_trajectories
+
+    name, sd, N, M, T, _ = WORKLOADS[workload]
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=seed)
+    return states, obs, controls
+
+
+def run_cpu_oracle(workload, n_sample, t_sample, repeats=1):
+    """The reference's CPU path (oracle port: eager PyTorch on the host cores) on a bounded sample of
+    the workload.  Returns (particle-steps/s, description)."""
+    from multimodalfilter_b200.synthetic import fill_parameters, synthetic_trajectories
+    from oracle import crossmodal_port as port
+
+    name, sd, _, M, _, _ = WORKLOADS[workload]
+    filt = fill_parameters(getattr(port, name)(), seed=0).eval()
+    is_pf = hasattr(filt, "num_particles")
+    if is_pf:
+        filt.num_particles = M
+    states, obs, controls = synthetic_trajectories(t_sample + 1, n_sample, sd, seed=0)
+    cov = (torch.eye(sd) * 0.1)[None].expand(n_sample, sd, sd)
+    best = None
+    for _ in range(repeats):
+        torch.manual_seed(0)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            filt.initialize_beliefs(mean=states[0], covariance=cov)
+            filt.forward_loop(observations={k: v[1:] for k, v in obs.items()}, controls=controls[1:])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    units = n_sample * (M if is_pf else 1) * t_sample
+    sample = f"{name} oracle port, eager PyTorch CPU fp32, forward_loop incl. observation encoders, N={n_sample} M={M} T={t_sample}"
+    return units / best, sample, best
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, sd, N, M, T, cfg = WORKLOADS[args.workload]
+    n_s, t_s = (8, 4) if args.workload == "c3" else (min(N, 32), min(T, 50))
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, sample, dt = run_cpu_oracle(args.workload, n_s, t_s)
+        if i >= args.warmup:
+            times.append(dt)
+    units = n_s * (M if "Particle" in name else 1) * t_s
+    ms = 1e3 * sum(times) / len(times)
+    value = units / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg, "bounded_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--resample-mode", default="multinomial")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference" or os.environ.get("MMF_BENCH_ALLOW_SHORT"), "W >= 3 warm-up steps"
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch.distributed as dist
+
+    from multimodalfilter_b200 import _lib, ops
+    from multimodalfilter_b200.crossmodal import models as M_
+    from multimodalfilter_b200.synthetic import fill_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().mmf_device_check())
+
+    name, sd, N, Mp, T, cfg = WORKLOADS[args.workload]
+    task = "push" if name.startswith("Push") else "door"
+    filt = fill_parameters(M_.MODEL_TYPES[task][name](), seed=0).to(dev).eval()
+    is_pf = hasattr(filt, "num_particles")
+    precision = args.precision or "fp32"
+    if is_pf:
+        filt.num_particles = Mp
+        filt.precision = precision
+        filt.resample_mode = args.resample_mode
+    units_per_pass = N * (Mp if is_pf else 1) * T
+
+    # every rank owns its own N trajectories (seeded by rank): weak scaling, no data-path collective
+    states, obs, controls = build_inputs(args.workload, seed=rank)
+    cov = (torch.eye(sd, device=dev) * 0.1)[None].expand(N, sd, sd).contiguous()
+    host_obs = {k: v[1:].contiguous().pin_memory() for k, v in obs.items()}
+    host_controls = controls[1:].contiguous().pin_memory()
+    host_mean0 = states[0].contiguous().pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_obs.values()) + host_controls.numel() * 4 + host_mean0.numel() * 4
+    host_out = torch.empty((T, N, sd), dtype=torch.float32).pin_memory()
+    d2h_bytes = host_out.numel() * 4
+
+    dev_obs = {k: v.to(dev) for k, v in host_obs.items()}
+    dev_controls = host_controls.to(dev)
+    dev_mean0 = host_mean0.to(dev)
+
+    # ---- device-resident pass: hoisted features computed once, outside the timed region ---------------
+    if is_pf:
+        plan = filt.fused_plan()
+        assert plan is not None
+        with torch.no_grad():
+            feats, modw = filt.hoist_observations(plan, dev_obs, T, N)
+        del dev_obs
+        torch.cuda.empty_cache()
+
+        def resident_pass():
+            with torch.no_grad():
+                filt.initialize_beliefs(mean=dev_mean0, covariance=cov)
+                est = None
+                for t in range(T):
+                    hoisted = ([None if f is None else f[t] for f in feats], None if modw is None else modw[t])
+                    est = filt.forward(observations=None, controls=dev_controls[t], _hoisted=hoisted)
+            return est
+    else:
+        filters = list(filt.filter_models)
+        with torch.no_grad():
+            zr = [f.sense_sequence(dev_obs, T, N) for f in filters]
+            z = torch.stack([a[0] for a in zr])
+            r = torch.stack([a[1] for a in zr])
+            beta = filt._sequence_weights(dev_obs, T, N, dev).transpose(0, 1).contiguous()
+        del dev_obs
+        torch.cuda.empty_cache()
+
+        def resident_pass():
+            with torch.no_grad():
+                filt.initialize_beliefs(mean=dev_mean0, covariance=cov)
+                means, covs = filt._advance(filters, dev_controls, z, r)
+                return ops.kf_fuse_crossmodal(means, covs, beta)[0]
+
+    def e2e_pass():
+        with torch.no_grad():
+            o = {k: v.to(dev, non_blocking=True) for k, v in host_obs.items()}
+            c = host_controls.to(dev, non_blocking=True)
+            m0 = host_mean0.to(dev, non_blocking=True)
+            filt.initialize_beliefs(mean=m0, covariance=cov)
+            est = filt.forward_loop(observations=o, controls=c)
+            host_out.copy_(est, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ops.PROFILE.reset(enabled=profile)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            start.record()
+            for _ in range(steps):
+                fn()
+            stop.record()
+            barrier()
+        ms = start.elapsed_time(stop)
+        prof = ops.PROFILE.collect() if profile else None
+        ops.PROFILE.reset(enabled=False)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, clk.summary(), prof
+
+    # inputs per pass (>= 100 MB of particle state + features) exceed nothing like L2 reuse across passes:
+    # every step rewrites the N*M particle set (C3: 49 MB states+weights per step, new noise each step).
+    ms_resident, clocks, prof = timed(resident_pass, args.steps, args.warmup, profile=True)
+    ms_e2e, clocks_e2e, _ = timed(e2e_pass, max(1, min(args.steps, 3)), 1)
+
+    value = world * units_per_pass / (ms_resident / 1e3)
+    e2e_value = world * units_per_pass / (ms_e2e / 1e3)
+
+    line = {
+        "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else precision,
+        "data": "synthetic",
+        "config": {"workload": cfg, "id": args.workload, "model": name, "trajectories_per_gpu": N, "particles": Mp,
+                   "filter_steps_per_pass": T, "resample": args.resample_mode if is_pf else None,
+                   "precision": precision,
+                   "l2": "working set per filter step (particle states + weights + noise, C3: 115 MB) exceeds nothing "
+                         "cached across passes: inputs larger than L2 over a pass; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "clocks": clocks_e2e},
+        "gpu_launches": prof["launches"] if prof else 0,
+    }
+
+    if rank == 0:
+        peaks = measured_peaks()
+        if is_pf and prof and prof["kernels"].get("pf_predict_measure"):
+            k = prof["kernels"]["pf_predict_measure"]
+            flops = FLOP_PER_PARTICLE_STEP[sd] * N * Mp
+            achieved = flops / (k["avg_ms"] / 1e3) / 1e12
+            line["roofline"] = {
+                "kernel": "k_particle_chain (mmf_pf_predict_measure)", "bound": "tensor", "achieved": achieved,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained", "avg_launch_ms": k["avg_ms"],
+                "share_of_step": k["total_ms"] / (ms_resident * args.steps),
+                "other_kernels": {n: {"avg_ms": v["avg_ms"], "share": v["total_ms"] / (ms_resident * args.steps)}
+                                  for n, v in prof["kernels"].items() if n != "pf_predict_measure"},
+            }
+            nr = prof["kernels"].get("pf_normalize_resample")
+            if nr:
+                bytes_ = N * Mp * (8 + 8 * sd + 8)  # logw r/w, states r/w, fp64 uniform
+                line["roofline"]["hbm_kernel"] = {
+                    "kernel": "k_normalize_resample", "bound": "hbm", "achieved": bytes_ / (nr["avg_ms"] / 1e3) / 1e9,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": bytes_ / (nr["avg_ms"] / 1e3) / 1e9 / peaks["hbm_gbs"]}
+        elif prof and prof["kernels"].get("ekf_loop"):
+            k = prof["kernels"]["ekf_loop"]
+            bytes_ = 340.0 * N * T  # 340 B / trajectory-step (K=2, sd=3)
+            achieved = bytes_ / (k["avg_ms"] / 1e3) / 1e9
+            line["roofline"] = {"kernel": "k_ekf_loop", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                                "avg_launch_ms": k["avg_ms"],
+                                "note": "latency/parallelism-bound by construction at N=256 (SURVEY.md section 7.6)"}
+        if not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            n_s, t_s = (8, 4) if args.workload == "c3" else (min(N, 32), min(T, 50))
+            rate, sample, dt = run_cpu_oracle(args.workload, n_s, t_s)
+            line["cpu_baseline"] = {"value": rate, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "sample": sample, "seconds": dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,21 @@ inline TrajRowsDev to_dev(const mmf_traj_rows& r) {
 
 int validate_chain(const mmf_chain& c, int sd, int out_dim, const char* what);
 
+// Opt the kernel in to the largest dynamic shared-memory window the device offers (227 KiB on
+// sm_100 minus the kernel's static shared memory); returns that window in *avail.
+template <typename Kernel>
+int opt_in_shared_memory(Kernel kernel, size_t* avail) {
+  int dev = 0, optin = 0;
+  MMF_CUDA(cudaGetDevice(&dev));
+  MMF_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  cudaFuncAttributes fa;
+  MMF_CUDA(cudaFuncGetAttributes(&fa, kernel));
+  const size_t window = (size_t)optin - fa.sharedSizeBytes;
+  MMF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)window));
+  *avail = window;
+  return MMF_OK;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -430,17 +430,19 @@ static int launch_ekf_sd(const EkfParams& P, cudaStream_t stream) {
   int wpc = (int)((pairs + sms - 1) / sms);
   wpc = wpc < 1 ? 1 : (wpc > EKF_MAX_WARPS ? EKF_MAX_WARPS : wpc);
   constexpr int WARP_FLOATS = 3 * (1 + SD) * U + 384;
+  static thread_local int configured_dev = -1;
+  static thread_local size_t window = 0;
+  if (configured_dev != dev) {
+    int rc = opt_in_shared_memory(k_ekf_loop<SD>, &window);
+    if (rc) return rc;
+    configured_dev = dev;
+  }
   size_t smem = ((size_t)((nf + 3) & ~3) + (size_t)wpc * WARP_FLOATS) * sizeof(float);
-  while (smem > 227 * 1024 && wpc > 1) {
+  while (smem > window && wpc > 1) {
     --wpc;
     smem = ((size_t)((nf + 3) & ~3) + (size_t)wpc * WARP_FLOATS) * sizeof(float);
   }
-  MMF_REQUIRE(smem <= 227 * 1024, "ekf: %zu B of shared memory needed", smem);
-  static thread_local int configured_dev = -1;
-  if (configured_dev != dev) {
-    MMF_CUDA(cudaFuncSetAttribute(k_ekf_loop<SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured_dev = dev;
-  }
+  MMF_REQUIRE(smem <= window, "ekf: %zu B of shared memory needed (window %zu B)", smem, window);
   int ctas = (P.N + wpc - 1) / wpc;
   const int max_ctas = (sms + P.F - 1) / P.F > 0 ? (sms / P.F > 0 ? sms / P.F : 1) : 1;
   if (ctas > max_ctas) ctas = max_ctas;

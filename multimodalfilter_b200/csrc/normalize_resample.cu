@@ -241,16 +241,19 @@ static size_t resample_smem_bytes(int M, bool soft) {
 int launch_normalize_resample(const ResampleParams& P, cudaStream_t stream) {
   const bool soft = P.alpha < 1.0f;
   const size_t smem = resample_smem_bytes(P.M, soft);
-  if (smem > 227 * 1024) {
-    set_error("normalize_resample: M=%d needs %zu B of shared memory; the large-M path is not built yet", P.M, smem);
-    return MMF_E_UNSUPPORTED;
-  }
   static thread_local int configured_dev = -1;
+  static thread_local size_t window = 0;
   int dev = 0;
   MMF_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    MMF_CUDA(cudaFuncSetAttribute(k_normalize_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int rc = opt_in_shared_memory(k_normalize_resample, &window);
+    if (rc) return rc;
     configured_dev = dev;
+  }
+  if (smem > window) {
+    set_error("normalize_resample: M=%d needs %zu B of shared memory (window %zu B); the large-M path is not built yet",
+              P.M, smem, window);
+    return MMF_E_UNSUPPORTED;
   }
   int sms = 148;
   MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -236,14 +236,16 @@ int launch_particle_chain_ffma(const mmf_pf_model* model, int N, int M, const fl
   for (int i = 0; i < MMF_MAX_SD * MMF_MAX_SD; ++i) P.q[i] = model->q_tril[i];
 
   const size_t smem = ((size_t)((maxf + 3) & ~3) + (size_t)U * TPB) * sizeof(float);
-  MMF_REQUIRE(smem <= 227 * 1024, "particle chain needs %zu B of shared memory (> 227 KiB)", smem);
   static thread_local int configured_dev = -1;
+  static thread_local size_t window = 0;
   int dev = 0;
   MMF_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    MMF_CUDA(cudaFuncSetAttribute(k_particle_chain_ffma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int rc = opt_in_shared_memory(k_particle_chain_ffma, &window);
+    if (rc) return rc;
     configured_dev = dev;
   }
+  MMF_REQUIRE(smem <= window, "particle chain needs %zu B of shared memory (window %zu B)", smem, window);
   int sms = 148;
   MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = (P.total + TPB - 1) / TPB;

@@ -30,6 +30,43 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 ESTIMATION = {"weighted_average": ESTIMATE_WEIGHTED_AVERAGE, "argmax": ESTIMATE_ARGMAX}
 
 
+class _Profile:
+    """Launch counter + optional per-entry-point CUDA-event timing (events are recorded on the
+    stream the kernels are launched on, i.e. torch's current stream).  Used by bench.py."""
+
+    def __init__(self):
+        self.enabled = False
+        self.launches = 0
+        self._events = {}
+
+    def reset(self, enabled=False):
+        self.enabled = enabled
+        self.launches = 0
+        self._events = {}
+
+    def run(self, name, kernels, fn, *args):
+        self.launches += kernels
+        if not self.enabled:
+            return fn(*args)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        rc = fn(*args)
+        stop.record()
+        self._events.setdefault(name, []).append((start, stop))
+        return rc
+
+    def collect(self):
+        torch.cuda.synchronize()
+        kernels = {}
+        for name, pairs in self._events.items():
+            ms = [a.elapsed_time(b) for a, b in pairs]
+            kernels[name] = {"count": len(ms), "total_ms": sum(ms), "avg_ms": sum(ms) / len(ms)}
+        return {"launches": self.launches, "kernels": kernels}
+
+
+PROFILE = _Profile()
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise _lib.MMFError(f"expected float32, got {t.dtype}")
@@ -49,7 +86,7 @@ def pf_init(mean, covariance, eps_MNsd):
     states = torch.empty((N, M, sd), device=mean.device, dtype=torch.float32)
     logw = torch.empty((N, M), device=mean.device, dtype=torch.float32)
     _lib.check(
-        lib.mmf_pf_init(N, M, sd, _lib.ptr(mean), _lib.ptr(covariance), _lib.ptr(eps_MNsd), _lib.ptr(states),
+        PROFILE.run("pf_init", 1, lib.mmf_pf_init, N, M, sd, _lib.ptr(mean), _lib.ptr(covariance), _lib.ptr(eps_MNsd), _lib.ptr(states),
                         _lib.ptr(logw), _lib.stream_of(mean))
     )
     return states, logw
@@ -66,7 +103,7 @@ def pf_traj_rows(model_struct, K, controls, obs_feats):
         arr[k] = None if feats[k] is None else feats[k].data_ptr()
     out = torch.empty((1 + K, N, _lib.UNITS), device=controls.device, dtype=torch.float32)
     _lib.check(
-        lib.mmf_pf_traj_rows(C.byref(model_struct), N, _lib.ptr(controls), arr, _lib.ptr(out), _lib.stream_of(controls))
+        PROFILE.run("pf_traj_rows", 1, lib.mmf_pf_traj_rows, C.byref(model_struct), N, _lib.ptr(controls), arr, _lib.ptr(out), _lib.stream_of(controls))
     )
     return out
 
@@ -87,7 +124,8 @@ def pf_predict_measure(model_struct, states, eps, rowbias, logw, modality_logw, 
     logw_out = torch.empty_like(logw)
     ll = torch.full((K, N, M), float("nan"), device=states.device, dtype=torch.float32) if want_ll else None
     _lib.check(
-        lib.mmf_pf_predict_measure(
+        PROFILE.run(
+            "pf_predict_measure", 1, lib.mmf_pf_predict_measure,
             C.byref(model_struct), N, M, _lib.ptr(states), _lib.ptr(eps), _lib.ptr(rowbias), _lib.ptr(logw),
             _lib.ptr(modality_logw), enabled_mask, precision, _lib.ptr(states_out), _lib.ptr(logw_out),
             _lib.ptr(ll), _lib.stream_of(states),
@@ -121,7 +159,8 @@ def pf_normalize_resample(states, logw_unnorm, *, estimation=ESTIMATE_WEIGHTED_A
     logits = torch.empty((N, M), device=dev, dtype=torch.float32) if (want_debug and resample) else None
     idx = torch.empty((N, M_out), device=dev, dtype=torch.int64) if (want_debug and resample) else None
     _lib.check(
-        lib.mmf_pf_normalize_resample(
+        PROFILE.run(
+            "pf_normalize_resample", 1, lib.mmf_pf_normalize_resample,
             N, M, sd, _lib.ptr(states), _lib.ptr(logw_unnorm), estimation, mode, float(alpha), M_out,
             _lib.ptr(uniforms), _lib.ptr(states_out), _lib.ptr(logw_out), _lib.ptr(est), _lib.ptr(logw_norm),
             _lib.ptr(logits), _lib.ptr(idx), None, _lib.stream_of(states),
@@ -140,7 +179,7 @@ def fuse_loglik(ll, w=None):
     ll = _f32c(ll)
     w = None if w is None else _f32c(w)
     out = torch.empty((N, M), device=ll.device, dtype=torch.float32)
-    _lib.check(lib.mmf_fuse_loglik(N, M, K, _lib.ptr(ll), _lib.ptr(w), _lib.ptr(out), _lib.stream_of(ll)))
+    _lib.check(PROFILE.run("fuse_loglik", 1, lib.mmf_fuse_loglik, N, M, K, _lib.ptr(ll), _lib.ptr(w), _lib.ptr(out), _lib.stream_of(ll)))
     return out
 
 
@@ -155,7 +194,7 @@ def resample_indices(logits, uniforms, mode=RESAMPLE_MULTINOMIAL_STRICT, M_out=N
         M_out = M if is_systematic(mode) else uniforms.shape[1]
     idx = torch.empty((N, M_out), device=logits.device, dtype=torch.int64)
     _lib.check(
-        lib.mmf_resample(N, M, M_out, _lib.ptr(logits), mode, _lib.ptr(uniforms), _lib.ptr(idx), None,
+        PROFILE.run("resample", 1, lib.mmf_resample, N, M, M_out, _lib.ptr(logits), mode, _lib.ptr(uniforms), _lib.ptr(idx), None,
                          _lib.stream_of(logits))
     )
     return idx
@@ -174,7 +213,7 @@ def ekf_loop(model_structs, mean0, cov0, controls, z, r_tril):
     means = torch.empty((F, T, N, sd), device=z.device, dtype=torch.float32)
     covs = torch.empty((F, T, N, sd, sd), device=z.device, dtype=torch.float32)
     _lib.check(
-        lib.mmf_ekf_loop_fwd(arr, F, T, N, _lib.ptr(mean0), _lib.ptr(cov0), _lib.ptr(controls), _lib.ptr(z),
+        PROFILE.run("ekf_loop", 1, lib.mmf_ekf_loop_fwd, arr, F, T, N, _lib.ptr(mean0), _lib.ptr(cov0), _lib.ptr(controls), _lib.ptr(z),
                              _lib.ptr(r_tril), _lib.ptr(means), _lib.ptr(covs), _lib.stream_of(z))
     )
     return means, covs
@@ -188,7 +227,7 @@ def dynamics_jacobian(model_struct, states, controls):
     pred = torch.empty_like(states)
     jac = torch.empty((N, sd, sd), device=states.device, dtype=torch.float32)
     _lib.check(
-        lib.mmf_dynamics_jacobian(C.byref(model_struct), N, _lib.ptr(states), _lib.ptr(controls), _lib.ptr(pred),
+        PROFILE.run("dynamics_jacobian", 1, lib.mmf_dynamics_jacobian, C.byref(model_struct), N, _lib.ptr(states), _lib.ptr(controls), _lib.ptr(pred),
                                   _lib.ptr(jac), _lib.stream_of(states))
     )
     return pred, jac
@@ -204,7 +243,7 @@ def kf_fuse_crossmodal(mu, P, beta):
     mean = torch.empty((*lead, sd), device=mu.device, dtype=torch.float32)
     cov = torch.empty((*lead, sd, sd), device=mu.device, dtype=torch.float32)
     _lib.check(
-        lib.mmf_kf_fuse_crossmodal(K, rows, sd, _lib.ptr(mu), _lib.ptr(P), _lib.ptr(beta), _lib.ptr(mean),
+        PROFILE.run("kf_fuse_crossmodal", 1, lib.mmf_kf_fuse_crossmodal, K, rows, sd, _lib.ptr(mu), _lib.ptr(P), _lib.ptr(beta), _lib.ptr(mean),
                                    _lib.ptr(cov), _lib.stream_of(mu))
     )
     return mean, cov
@@ -220,7 +259,7 @@ def kf_fuse_unimodal(mu, P):
     mean = torch.empty((*lead, sd), device=mu.device, dtype=torch.float32)
     cov = torch.empty((*lead, sd, sd), device=mu.device, dtype=torch.float32)
     _lib.check(
-        lib.mmf_kf_fuse_unimodal(K, rows, sd, _lib.ptr(mu), _lib.ptr(P), _lib.ptr(mean), _lib.ptr(cov),
+        PROFILE.run("kf_fuse_unimodal", 1, lib.mmf_kf_fuse_unimodal, K, rows, sd, _lib.ptr(mu), _lib.ptr(P), _lib.ptr(mean), _lib.ptr(cov),
                                  _lib.stream_of(mu))
     )
     return mean, cov

@@ -10,6 +10,11 @@ if REPO not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    import torch
+
+    # parity runs compare against an fp32 CPU oracle: keep library convs / matmuls in true fp32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 @pytest.fixture(scope="session")

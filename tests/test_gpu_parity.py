@@ -1,0 +1,426 @@
+"""Parity of the CUDA path (called through the C ABI) against the oracle, on identical inputs and
+identical random draws.  Bar (BASELINE.json north_star): resampling indices BIT-EXACT; states,
+covariances and log-likelihoods within 1e-4 relative in fp32 (see util.assert_close)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import crossmodal_port as port  # noqa: E402
+from oracle import pinned  # noqa: E402
+from oracle.golden_cases import run_all  # noqa: E402
+from oracle.noise import RecordedNoise  # noqa: E402
+
+from multimodalfilter_b200 import _lib, fused, ops  # noqa: E402
+from multimodalfilter_b200.crossmodal import models as M  # noqa: E402
+from multimodalfilter_b200.synthetic import fill_parameters, synthetic_trajectories  # noqa: E402
+
+from util import ReplayNoise, assert_close, draw_noise  # noqa: E402
+
+DEV = "cuda:0"
+RTOL = 1e-4
+
+
+def _product(name):
+    for task in M.MODEL_TYPES.values():
+        if name in task:
+            return task[name]
+    return getattr(M, name)
+
+
+def test_device_is_sm100_and_library_loads():
+    lib = _lib.load()
+    _lib.check(lib.mmf_device_check())
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+# ---- R2 ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,M,sd", [(5, 30, 2), (3, 300, 3), (1, 1, 2), (4096, 100, 2)])
+def test_pf_init(N, M, sd):
+    g = torch.Generator().manual_seed(N + M)
+    mean = torch.randn(N, sd, generator=g)
+    A = torch.randn(N, sd, sd, generator=g)
+    cov = A @ A.transpose(-1, -2) + 0.1 * torch.eye(sd)
+    eps = torch.randn(M, N, sd, generator=g)
+    states, logw = ops.pf_init(mean.to(DEV), cov.to(DEV), eps.to(DEV))
+    ref = (mean[None] + (torch.linalg.cholesky(cov)[None] @ eps[..., None]).squeeze(-1)).transpose(0, 1)
+    assert_close(states.cpu(), ref, RTOL, msg="particle_states")
+    assert torch.equal(logw.cpu(), torch.full((N, M), -math.log(M)))
+
+
+# ---- R5 standalone -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,M,K,weighted", [(4, 7, 2, True), (3, 1000, 2, False), (2, 5, 3, True), (1, 1, 1, False)])
+def test_fuse_loglik(N, M, K, weighted):
+    g = torch.Generator().manual_seed(7)
+    ll = torch.randn(N, M, K, generator=g) * 5
+    w = torch.randn(N, K, generator=g) if weighted else None
+    if weighted and K > 1:
+        w[0, 0] = -float("inf")  # quirk Q3 blackout weight
+    out = ops.fuse_loglik(ll.to(DEV), None if w is None else w.to(DEV))
+    ref = torch.logsumexp(ll if w is None else w[:, None, :] + ll, dim=2)
+    assert_close(out.cpu(), ref, RTOL, msg="fused log-likelihood")
+
+
+# ---- R7 standalone: bit-exact indices ------------------------------------------------------------------
+RESAMPLE_CASES = [(8, 30, 30), (4, 300, 300), (6, 1000, 1000), (3, 257, 64), (2, 1, 5), (5, 2, 9), (2, 4096, 4096), (1, 10000, 777)]
+
+
+@pytest.mark.parametrize("mode", ["multinomial", "multinomial_fast", "systematic", "systematic_fast"])
+@pytest.mark.parametrize("N,M,S", RESAMPLE_CASES)
+def test_resample_indices_bit_exact(mode, N, M, S):
+    g = torch.Generator().manual_seed(1000 * N + M)
+    logits = torch.randn(N, M, generator=g) * 4
+    logits = logits - torch.logsumexp(logits, dim=1, keepdim=True)
+    if M > 3:
+        logits[0, 1] = -float("inf")      # a dead particle
+        logits[-1, : M // 2] = -200.0     # underflowing mass
+    u = torch.rand(N, generator=g, dtype=torch.float64) if mode.startswith("systematic") else \
+        torch.rand(N, S, generator=g, dtype=torch.float64)
+    idx = ops.resample_indices(logits.to(DEV), u.to(DEV), mode=ops.RESAMPLE_MODES[mode], M_out=S).cpu().numpy()
+    ref = pinned.resample(logits.numpy(), u.numpy(), mode, num_samples=S)
+    assert idx.shape == ref.shape == (N, S)
+    assert np.array_equal(idx, ref), f"{(idx != ref).sum()} / {idx.size} indices differ"
+    assert idx.min() >= 0 and idx.max() < M
+    if M > 3:
+        assert not (idx[0] == 1).any()  # the dead particle is never drawn
+
+
+def test_resample_degenerate_distributions():
+    M = 64
+    logits = torch.full((3, M), -float("inf"))
+    logits[0, 17] = 0.0                      # one-hot
+    logits[1] = -math.log(M)                 # exactly uniform
+    logits[2, [3, 60]] = math.log(0.5)       # two atoms
+    u = torch.rand(3, M, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    for mode in ("multinomial", "multinomial_fast"):
+        idx = ops.resample_indices(logits.to(DEV), u.to(DEV), mode=ops.RESAMPLE_MODES[mode]).cpu()
+        assert (idx[0] == 17).all()
+        assert set(idx[2].tolist()) <= {3, 60}
+        assert np.array_equal(idx.numpy(), pinned.resample(logits.numpy(), u.numpy(), mode))
+    u0 = torch.tensor([0.25, 0.5, 0.999], dtype=torch.float64)
+    idx = ops.resample_indices(logits.to(DEV), u0.to(DEV), mode=ops.RESAMPLE_SYSTEMATIC_STRICT).cpu()
+    assert torch.equal(idx[1], torch.arange(M))  # uniform weights + systematic = identity
+
+
+def test_pinned_arithmetic_differs_from_torch_only_at_cdf_ties():
+    """The pinned CDF and torch.multinomial's CPU CDF agree except where a uniform falls within
+    rounding distance of a CDF step (hard part 1c)."""
+    N, M = 64, 1000
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(N, M, generator=g) * 3
+    logits = logits - torch.logsumexp(logits, dim=1, keepdim=True)
+    u = torch.rand(N, M, generator=g, dtype=torch.float64)
+    idx = ops.resample_indices(logits.to(DEV), u.to(DEV)).cpu().numpy()
+    probs = torch.softmax(logits, dim=-1)
+    from torchfilter.filters import multinomial_inverse_cdf
+
+    ref = multinomial_inverse_cdf(probs, u).numpy()
+    diff = np.argwhere(idx != ref)
+    assert len(diff) < 1e-3 * idx.size
+    cdf = np.cumsum(probs.numpy().astype(np.float64), axis=1)
+    for n, j in diff:
+        lo, hi = sorted((idx[n, j], ref[n, j]))
+        assert hi - lo == 1 and abs(cdf[n, lo] - u[n, j].item()) < 2e-6
+
+
+# ---- R6 + R7 fused kernel ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["none", "multinomial", "multinomial_fast", "systematic"])
+@pytest.mark.parametrize("N,M,sd,M_out,alpha,estimation", [
+    (6, 30, 2, 30, 1.0, "weighted_average"),
+    (4, 300, 3, 300, 1.0, "weighted_average"),
+    (3, 1000, 2, 1000, 1.0, "argmax"),
+    (5, 30, 2, 300, 1.0, "weighted_average"),   # eval after train: particle count grows (quirk Q8)
+    (4, 100, 3, 100, 0.5, "weighted_average"),  # soft resampling
+    (2, 1, 2, 1, 1.0, "weighted_average"),
+])
+def test_normalize_estimate_resample(mode, N, M, sd, M_out, alpha, estimation):
+    if mode == "none" and (M_out != M or alpha != 1.0):
+        pytest.skip("no resampling: count / alpha irrelevant")
+    g = torch.Generator().manual_seed(N * M + sd)
+    states = torch.randn(N, M, sd, generator=g)
+    logw_unnorm = torch.randn(N, M, generator=g) * 3 - 5
+    code = ops.RESAMPLE_NONE if mode == "none" else ops.RESAMPLE_MODES[mode]
+    u = None
+    if mode != "none":
+        u = torch.rand(N, generator=g, dtype=torch.float64) if mode.startswith("systematic") else \
+            torch.rand(N, M_out, generator=g, dtype=torch.float64)
+    out = ops.pf_normalize_resample(states.to(DEV), logw_unnorm.to(DEV), estimation=ops.ESTIMATION[estimation],
+                                    mode=code, alpha=alpha, M_out=M_out, uniforms=None if u is None else u.to(DEV),
+                                    want_debug=True)
+    logw = logw_unnorm - torch.logsumexp(logw_unnorm, dim=1, keepdim=True)
+    assert_close(out["logw_norm"].cpu(), logw, RTOL, msg="normalised log-weights")
+    if estimation == "weighted_average":
+        est = torch.sum(torch.exp(logw)[:, :, None] * states, dim=1)
+        assert_close(out["estimate"].cpu(), est, RTOL, msg="estimate")
+    else:
+        best = torch.argmax(logw, dim=1)
+        assert torch.equal(out["estimate"].cpu(), states[torch.arange(N), best])
+    if mode == "none":
+        assert_close(out["logw"].cpu(), logw, RTOL, msg="log-weights")
+        return
+    if alpha < 1.0:
+        uniform = torch.full((N, M), -math.log(M))
+        logits = torch.logsumexp(torch.stack([logw + math.log(alpha), uniform + math.log(1 - alpha)]), dim=0)
+        assert_close(out["logits"].cpu(), logits, RTOL, msg="soft-resampling logits")
+    # indices: bit-exact against the pinned arithmetic applied to the kernel's own logits
+    ref_idx = pinned.resample(out["logits"].cpu().numpy(), u.numpy(), mode, num_samples=M_out)
+    idx = out["idx"].cpu().numpy()
+    assert np.array_equal(idx, ref_idx), f"{(idx != ref_idx).sum()} / {idx.size} indices differ"
+    gathered = torch.gather(states, 1, torch.from_numpy(idx)[:, :, None].expand(N, M_out, sd))
+    assert torch.equal(out["states"].cpu(), gathered)  # a gather moves bits, it must be exact
+    if alpha < 1.0:
+        new_logw = torch.gather(out["logw_norm"].cpu() - out["logits"].cpu(), 1, torch.from_numpy(idx))
+        assert_close(out["logw"].cpu(), new_logw, 1e-5, msg="soft-resampled log-weights")
+    else:
+        assert torch.equal(out["logw"].cpu(), torch.full((N, M_out), -math.log(M)))
+
+
+# ---- R3 + R4 + R5 per-particle chain -------------------------------------------------------------------
+@pytest.mark.parametrize("name,sd,flags", [
+    ("PushCrossmodalParticleFilter", 2, [True, True]),
+    ("PushCrossmodalParticleFilter", 2, [False, True]),
+    ("PushCrossmodalParticleFilterSeq5", 2, [True, True]),
+    ("DoorCrossmodalParticleFilter", 3, [True, True]),
+    ("PushUnimodalParticleFilter", 2, [True, True]),
+    ("DoorUnimodalParticleFilter", 3, [True, False]),
+    ("PushParticleFilter", 2, None),
+])
+@pytest.mark.parametrize("N,Mp", [(5, 30), (3, 300), (2, 1000)])
+def test_predict_measure_matches_oracle_modules(name, sd, flags, N, Mp):
+    oracle_f = fill_parameters(getattr(port, name)(), seed=21).eval()
+    prod_f = fill_parameters(_product(name)(), seed=21).to(DEV).eval()
+    if flags is not None:
+        oracle_f.measurement_model.enabled_models = list(flags)
+        prod_f.measurement_model.enabled_models = list(flags)
+    g = torch.Generator().manual_seed(5 * N + Mp)
+    states = torch.randn(N, Mp, sd, generator=g)
+    logw = torch.randn(N, Mp, generator=g) - 3
+    eps = torch.randn(N * Mp, sd, generator=g)
+    _, obs, controls = synthetic_trajectories(1, N, sd, seed=31, blackout_fraction=0.4 if "Seq5" in name else 0.0)
+    obs0, u0 = {k: v[0] for k, v in obs.items()}, controls[0]
+
+    with torch.no_grad():
+        pred, trils = oracle_f.dynamics_model(initial_states=states.reshape(-1, sd),
+                                              controls=u0.repeat_interleave(Mp, dim=0))
+        moved = (pred + (trils @ eps[..., None]).squeeze(-1)).view(N, Mp, sd)
+        ll = oracle_f.measurement_model(states=moved, observations=obs0)
+        ref_logw = logw + ll
+
+    plan = fused.PFPlan.build(prod_f)
+    assert plan is not None
+    plan.refresh(torch.device(DEV))
+    obs_d = {k: v.to(DEV) for k, v in obs0.items()}
+    with torch.no_grad():
+        feats = plan.head_features(obs_d)
+        modw = plan.modality_log_weights(obs_d)
+    rowbias = ops.pf_traj_rows(plan.struct, plan.K, u0.to(DEV), feats)
+    moved_k, logw_k, ll_k = ops.pf_predict_measure(plan.struct, states.to(DEV), eps.to(DEV), rowbias, logw.to(DEV),
+                                                   modw, plan.enabled_mask(), precision=ops.PREC_FP32, want_ll=True)
+    assert_close(moved_k.cpu(), moved, RTOL, msg="moved particle states")
+    assert_close(logw_k.cpu(), ref_logw, RTOL, msg="un-normalised log-weights")
+    # per-head log-likelihoods against the oracle's individual heads
+    mm = oracle_f.measurement_model
+    heads = list(mm.measurement_models) if hasattr(mm, "measurement_models") else [mm]
+    for k, head in enumerate(heads):
+        if flags is not None and not flags[k]:
+            assert torch.isnan(ll_k[k]).all()  # never written
+            continue
+        with torch.no_grad():
+            assert_close(ll_k[k].cpu(), head(states=moved, observations=obs0), RTOL, msg=f"head {k} log-likelihood")
+
+
+# ---- golden fixture (generated by the reference's own code) ---------------------------------------
+@pytest.mark.parametrize("group", ["dyn/", "head/", "fuse/", "vsensor/", "kf/"])
+def test_product_matches_reference_fixture(golden, group):
+    got = run_all(_product, device=DEV, include_rng_cases=False, only=[group])
+    keys = [k for k in golden if k.startswith(group)]
+    assert sorted(got) == sorted(keys)
+    for k in keys:
+        assert_close(got[k], golden[k], RTOL, msg=k)
+
+
+# ---- whole recursion, PF ---------------------------------------------------------------------------------
+def _run_pair(name, sd, N, Mp, T, train, mode="multinomial", seed=3):
+    init, eps, us = draw_noise(T, N, Mp, sd, seed=seed, systematic=mode.startswith("systematic"))
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=seed + 1)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd)
+
+    o = fill_parameters(getattr(port, name)(), seed=22)
+    o.train(train)
+    o.num_particles = Mp
+    o.noise = RecordedNoise(init_eps=init, process_eps=eps, uniforms=us, mode=mode, arithmetic="pinned")
+    with torch.no_grad():
+        o.initialize_beliefs(mean=states[0], covariance=cov)
+        ref = o.forward_loop(observations={k: v[1:] for k, v in obs.items()}, controls=controls[1:])
+
+    p = fill_parameters(_product(name)(), seed=22).to(DEV)
+    p.train(train)
+    p.num_particles = Mp
+    p.resample_mode = mode
+    p.noise = ReplayNoise(init_eps=init, process_eps=eps, uniforms=us)
+    with torch.no_grad():
+        p.initialize_beliefs(mean=states[0].to(DEV), covariance=cov.to(DEV).contiguous())
+        got = p.forward_loop(observations={k: v[1:].to(DEV) for k, v in obs.items()}, controls=controls[1:].to(DEV))
+    return o, ref, p, got
+
+
+@pytest.mark.parametrize("name,sd", [("PushCrossmodalParticleFilter", 2), ("DoorCrossmodalParticleFilter", 3),
+                                     ("PushUnimodalParticleFilter", 2)])
+def test_forward_loop_train_mode_no_resampling(name, sd):
+    o, ref, p, got = _run_pair(name, sd, N=6, Mp=30, T=8, train=True)
+    assert_close(got.cpu(), ref, RTOL, msg="estimates")
+    assert_close(p.particle_states.cpu(), o.particle_states, RTOL, msg="particle states")
+    assert_close(p.particle_log_weights.cpu(), o.particle_log_weights, RTOL, msg="particle log-weights")
+
+
+@pytest.mark.parametrize("mode", ["multinomial", "multinomial_fast", "systematic"])
+@pytest.mark.parametrize("name,sd,Mp", [("PushCrossmodalParticleFilter", 2, 30), ("DoorCrossmodalParticleFilter", 3, 300)])
+def test_filter_steps_eval_mode_with_resampling(name, sd, Mp, mode):
+    """BASELINE config C1 in miniature: crossmodal PF eval, resampling every step, identical draws.
+
+    Both filters start every step from the SAME particle set (the oracle's), so float differences
+    cannot compound through resampling.  Estimates must agree to 1e-4; resampling indices must be
+    identical, except where a uniform sits within rounding distance of a CDF step -- there the
+    1e-6-level difference between the CPU oracle's and the kernel's *logits* may pick the
+    neighbouring particle; every such case is checked to be exactly that (and they are rare)."""
+    N, T = 8, 10
+    init, eps, us = draw_noise(T, N, Mp, sd, seed=3, systematic=mode.startswith("systematic"))
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=4)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd)
+    o = fill_parameters(getattr(port, name)(), seed=22).eval()
+    o.num_particles = Mp
+    o.noise = RecordedNoise(init_eps=init, process_eps=eps, uniforms=us, mode=mode, arithmetic="pinned")
+    p = fill_parameters(_product(name)(), seed=22).to(DEV).eval()
+    p.num_particles = Mp
+    p.resample_mode = mode
+    p.noise = ReplayNoise(init_eps=init, process_eps=eps, uniforms=us)
+    p.debug = {}
+    draws = flips = 0
+    with torch.no_grad():
+        o.initialize_beliefs(mean=states[0], covariance=cov)
+        p.initialize_beliefs(mean=states[0].to(DEV), covariance=cov.to(DEV).contiguous())
+        assert_close(p.particle_states.cpu(), o.particle_states, RTOL, msg="initial particles")
+        for t in range(T):
+            p.particle_states = o.particle_states.to(DEV).contiguous()
+            p.particle_log_weights = o.particle_log_weights.to(DEV).contiguous()
+            obs_t = {k: v[1 + t] for k, v in obs.items()}
+            est_o = o(observations=obs_t, controls=controls[1 + t])
+            est_p = p(observations={k: v.to(DEV) for k, v in obs_t.items()}, controls=controls[1 + t].to(DEV))
+            assert_close(est_p.cpu(), est_o, RTOL, msg=f"estimate at step {t}")
+            idx_o, idx_p = o.noise.indices[-1], p.debug["idx"].cpu()
+            same = (idx_o == idx_p).all(dim=1)
+            draws += idx_o.numel()
+            if not same.all():
+                # prove each differing draw is a CDF tie on the kernel's own logits
+                u = us[t].numpy()
+                _, cdf = pinned.resample(p.debug["logits"].cpu().numpy(), u, mode, num_samples=Mp, return_cdf=True)
+                for n, j in np.argwhere((idx_o != idx_p).numpy()):
+                    flips += 1
+                    lo, hi = sorted((int(idx_o[n, j]), int(idx_p[n, j])))
+                    assert hi - lo == 1, "indices differ by more than one slot"
+                    uj = (u[n] + j) / Mp if mode.startswith("systematic") else u[n, j]
+                    assert abs(cdf[n, lo] / cdf[n, -1] - uj) < 5e-6, "index differs away from a CDF tie"
+            assert_close(p.particle_states.cpu()[same], o.particle_states[same], RTOL, msg=f"resampled states, step {t}")
+            assert torch.equal(p.particle_log_weights.cpu(), o.particle_log_weights)
+    assert flips <= max(2, draws // 5000), f"{flips} tie flips in {draws} draws"
+
+
+def test_single_step_forward_equals_forward_loop():
+    name, sd, N, Mp, T = "PushCrossmodalParticleFilter", 2, 4, 30, 4
+    init, eps, us = draw_noise(T, N, Mp, sd, seed=9)
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=10)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd).to(DEV).contiguous()
+    outs = []
+    for use_loop in (True, False):
+        p = fill_parameters(_product(name)(), seed=23).to(DEV).eval()
+        p.num_particles = Mp
+        p.noise = ReplayNoise(init_eps=init, process_eps=eps, uniforms=us)
+        with torch.no_grad():
+            p.initialize_beliefs(mean=states[0].to(DEV), covariance=cov)
+            o_d = {k: v[1:].to(DEV) for k, v in obs.items()}
+            if use_loop:
+                outs.append(p.forward_loop(observations=o_d, controls=controls[1:].to(DEV)))
+            else:
+                outs.append(torch.stack([p(observations={k: v[t] for k, v in o_d.items()},
+                                           controls=controls[1 + t].to(DEV)) for t in range(T)]))
+    # the hoisted encoders run on T*N rows, the per-step ones on N rows: library GEMMs may block differently
+    assert_close(outs[0].cpu(), outs[1].cpu(), 1e-5, msg="hoisted vs per-step")
+
+
+# ---- whole recursion, EKF (BASELINE config C2 in miniature) -------------------------------------------
+@pytest.mark.parametrize("name,sd", [("DoorCrossmodalKalmanFilter", 3), ("PushCrossmodalKalmanFilter", 2),
+                                     ("DoorUnimodalKalmanFilter", 3), ("DoorKalmanFilter", 3)])
+def test_ekf_forward_loop_matches_oracle(name, sd):
+    T, N = 20, 16
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=12)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd)
+    o = fill_parameters(getattr(port, name)(), seed=24).eval()
+    with torch.no_grad():
+        o.initialize_beliefs(mean=states[0], covariance=cov)
+        ref = o.forward_loop(observations={k: v[1:] for k, v in obs.items()}, controls=controls[1:])
+    p = fill_parameters(_product(name)(), seed=24).to(DEV).eval()
+    with torch.no_grad():
+        p.initialize_beliefs(mean=states[0].to(DEV), covariance=cov.to(DEV).contiguous())
+        got = p.forward_loop(observations={k: v[1:].to(DEV) for k, v in obs.items()}, controls=controls[1:].to(DEV))
+    assert_close(got.cpu(), ref, RTOL, msg="EKF estimates")
+    ocov = getattr(o, "weighted_covariances", None)
+    pcov = getattr(p, "weighted_covariances", None)
+    if ocov is not None and pcov is not None:
+        assert_close(pcov.cpu(), ocov, RTOL, msg="fused covariance")
+    of = list(o.filter_models) if hasattr(o, "filter_models") else [o]
+    pf = list(p.filter_models) if hasattr(p, "filter_models") else [p]
+    for a, b in zip(of, pf):
+        assert_close(b.belief_mean.cpu(), a.belief_mean, RTOL, msg="unimodal belief mean")
+        assert_close(b.belief_covariance.cpu(), a.belief_covariance, RTOL, msg="unimodal belief covariance")
+
+
+def test_dynamics_jacobian_kernel_matches_autograd():
+    dyn_o = fill_parameters(port.DoorDynamicsModel(), seed=25)
+    dyn_p = fill_parameters(M.DoorDynamicsModel(), seed=25).to(DEV)
+    x, u = torch.randn(33, 3), torch.randn(33, 7)
+    ref = dyn_o.jacobian(initial_states=x, controls=u).detach()
+    with torch.no_grad():
+        got = dyn_p.jacobian(initial_states=x.to(DEV), controls=u.to(DEV))
+    assert_close(got.cpu(), ref, RTOL, msg="dynamics Jacobian")
+
+
+# ---- size-independent properties at BASELINE sizes -----------------------------------------------------
+def test_full_size_step_properties_and_shard_invariance():
+    """Config C3 shape (N=4096, M=1000, sd=2), one step: normalised weights, sortedness of
+    systematic indices, and trajectory-sharded == unsharded bit-for-bit."""
+    N, Mp, sd = 4096, 1000, 2
+    p = fill_parameters(M.PushUnimodalParticleFilter(), seed=26).to(DEV).eval()
+    plan = fused.PFPlan.build(p)
+    plan.refresh(torch.device(DEV))
+    g = torch.Generator(device=DEV).manual_seed(0)
+    states = torch.randn(N, Mp, sd, device=DEV, generator=g)
+    logw = torch.full((N, Mp), -math.log(Mp), device=DEV)
+    eps = torch.randn(N * Mp, sd, device=DEV, generator=g)
+    controls = torch.randn(N, 7, device=DEV, generator=g)
+    feats = [torch.randn(N, 64, device=DEV, generator=g), torch.randn(N, 128, device=DEV, generator=g)]
+    u = torch.rand(N, device=DEV, dtype=torch.float64, generator=g)
+
+    def step(lo, hi):
+        rb = ops.pf_traj_rows(plan.struct, 2, controls[lo:hi], [f[lo:hi] for f in feats])
+        moved, lw = ops.pf_predict_measure(plan.struct, states[lo:hi], eps[lo * Mp:hi * Mp], rb, logw[lo:hi], None, 3)
+        out = ops.pf_normalize_resample(moved, lw, mode=ops.RESAMPLE_SYSTEMATIC_FAST, uniforms=u[lo:hi], want_debug=True)
+        return moved, lw, out
+
+    moved, lw, out = step(0, N)
+    assert torch.isfinite(moved).all() and torch.isfinite(lw).all()
+    total = torch.exp(out["logw_norm"].double()).sum(dim=1)
+    assert (total - 1).abs().max() < 1e-4
+    idx = out["idx"]
+    assert (idx[:, 1:] >= idx[:, :-1]).all() and idx.min() >= 0 and idx.max() < Mp
+    counts = torch.zeros(N, Mp, device=DEV).scatter_add_(1, idx, torch.ones_like(idx, dtype=torch.float32))
+    expected = torch.exp(out["logw_norm"]) * Mp
+    assert (counts - expected).abs().max() <= 1.0 + 1e-3  # systematic resampling: |count - M w| <= 1
+    half = N // 2
+    a, b = step(0, half), step(half, N)
+    assert torch.equal(torch.cat([a[0], b[0]]), moved)
+    assert torch.equal(torch.cat([a[1], b[1]]), lw)
+    for key in ("states", "estimate", "idx", "logw_norm"):
+        assert torch.equal(torch.cat([a[2][key], b[2][key]]), out[key]), key
