@@ -1,24 +1,515 @@
-// particle_chain_tc.cu -- tcgen05 / TMEM build of the per-particle MLP chain (placeholder until
-// the tensor-core path lands; the FP32 CUDA-core chain in particle_chain_ffma.cu is the parity build).
+// particle_chain_tc.cu -- R3 + R4 + R5 + first half of R6 on the 5th-generation tensor cores
+// (MMF_PREC_BF16X3 / MMF_PREC_BF16): the throughput build of the per-particle MLP chain.
+//
+// Layout of the computation (one persistent CTA per SM, 4 groups x 128 threads):
+//   * a group owns one TILE of 128 particles at a time; thread r of the group owns particle r of
+//     the tile for the whole chain, and TMEM lane r;
+//   * every 64->64 layer is D[128x64] (TMEM, fp32) = A[128x64] (TMEM, bf16) x W^T (smem, bf16,
+//     K-major SWIZZLE_128B), issued by ONE thread as tcgen05.mma.cta_group::1.kind::f16 with the
+//     A operand read from tensor memory (TS form);
+//   * fp32-grade accuracy comes from split operands: a = a_hi + a_lo, w = w_hi + w_lo (bf16 each),
+//     D = a_hi w_hi + a_hi w_lo + a_lo w_hi  (3 MMAs per K step, fp32 accumulate) -- MMF_PREC_BF16X3;
+//     MMF_PREC_BF16 issues only the first product;
+//   * the epilogue (tcgen05.ld -> +bias / +per-trajectory row / +residual -> ReLU -> bf16 split ->
+//     tcgen05.st of the next layer's A operand) runs on the group's own 128 threads, so activations
+//     never leave the SM: no shared-memory or HBM round trip between layers;
+//   * the 4 groups are independent pipelines: while one group's accumulator is in the tensor pipe
+//     the other three run their epilogues on the CUDA cores;
+//   * weights: one chain at a time is resident in shared memory (dynamics 148 KiB, a head 116 KiB,
+//     both bf16 halves), brought in by cp.async.bulk (TMA, mbarrier complete_tx) once per phase;
+//     the kernel makes one pass over its tiles per chain ("phase"): dynamics -> moved state to HBM
+//     -> head 0 -> running fused log-likelihood to HBM -> head 1 ... (+24 B/particle of traffic,
+//     three orders of magnitude below the tensor time).
+//
+// Replaces the same reference lines as particle_chain_ffma.cu.
+#include <cuda_bf16.h>
+
 #include "kernels.cuh"
 
 namespace mmf {
 
-size_t chain_mma_bytes(const mmf_chain* chain) {
-  (void)chain;
-  return 0;
+constexpr int TC_GROUPS = 4;
+constexpr int TC_THREADS = TC_GROUPS * 128;
+constexpr int TILE_B = 64 * 128;      // one 64(N) x 64(K) bf16 operand tile: 64 rows of 128 bytes
+constexpr int OUT_TILE_B = 16 * 128;  // the output layer, N padded to 16
+constexpr int OUT_PAD = 16;
+
+// ---- image of one chain as it sits in shared memory (built once by k_pack_chain_mma) --------------
+//   [layer 0 hi | layer 0 lo | ... | layer L-1 hi | layer L-1 lo | out hi | out lo]   bf16, SW128 K-major
+//   [in_Wt[in_dim][64] | in_b[64] | bias[L][64] (zeros for the mid layer) | out_b[16]]  fp32
+__host__ __device__ inline int chain_layers(const ChainDev& c) { return 2 * c.n_pre + 1 + 2 * c.n_post; }
+__host__ __device__ inline size_t image_tiles_bytes(const ChainDev& c) {
+  return (size_t)chain_layers(c) * 2 * TILE_B + 2 * OUT_TILE_B;
 }
+__host__ __device__ inline size_t image_bytes(const ChainDev& c) {
+  return image_tiles_bytes(c) + sizeof(float) * (size_t)(c.in_dim * U + U + chain_layers(c) * U + OUT_PAD);
+}
+
+// byte offset of element (n, k) inside a K-major SWIZZLE_128B tile whose rows are 64 bf16 = 128 B
+__host__ __device__ inline int sw128_offset(int n, int k) {
+  return (n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+
+__global__ void k_pack_chain_mma(ChainDev ch, uint8_t* __restrict__ dst) {
+  const int L = chain_layers(ch);
+  const float* w = ch.w;
+  // fp32 pack offsets (include/mmf_b200.h): in, pre-res, mid, post-res, out
+  const int off_in = 0;
+  const int off_first_res = ch.in_dim * U + U;
+  const int off_mid = off_first_res + ch.n_pre * RES_FLOATS;
+  const int off_post = off_mid + U * U;
+  const int off_out = off_post + ch.n_post * RES_FLOATS;
+  float* fdst = reinterpret_cast<float*>(dst + image_tiles_bytes(ch));
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+
+  for (int layer = 0; layer < L; ++layer) {
+    const float* Wt;  // transposed [k][j]
+    const float* b;   // may be null (mid layer: bias lives in the per-trajectory row)
+    if (layer < 2 * ch.n_pre) {
+      const float* r = w + off_first_res + (layer >> 1) * RES_FLOATS;
+      Wt = r + (layer & 1) * (U * U + U);
+      b = Wt + U * U;
+    } else if (layer == 2 * ch.n_pre) {
+      Wt = w + off_mid;
+      b = nullptr;
+    } else {
+      const int rel = layer - 2 * ch.n_pre - 1;
+      const float* r = w + off_post + (rel >> 1) * RES_FLOATS;
+      Wt = r + (rel & 1) * (U * U + U);
+      b = Wt + U * U;
+    }
+    uint8_t* hi = dst + (size_t)layer * 2 * TILE_B;
+    uint8_t* lo = hi + TILE_B;
+    for (int e = tid; e < U * U; e += nth) {
+      const int n = e / U, k = e % U;  // B[n][k] = W[n][k] = Wt[k][n]
+      const float v = Wt[k * U + n];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      const int o = sw128_offset(n, k);
+      *reinterpret_cast<__nv_bfloat16*>(hi + o) = h;
+      *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
+    }
+    for (int j = tid; j < U; j += nth) fdst[ch.in_dim * U + U + layer * U + j] = b ? b[j] : 0.0f;
+  }
+  {  // output layer: out_W[out_dim][64] row-major, rows >= out_dim are zero
+    uint8_t* hi = dst + (size_t)L * 2 * TILE_B;
+    uint8_t* lo = hi + OUT_TILE_B;
+    const float* W = w + off_out;
+    for (int e = tid; e < OUT_PAD * U; e += nth) {
+      const int n = e / U, k = e % U;
+      const float v = n < ch.out_dim ? W[n * U + k] : 0.0f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      const int o = sw128_offset(n, k);
+      *reinterpret_cast<__nv_bfloat16*>(hi + o) = h;
+      *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
+    }
+    for (int j = tid; j < OUT_PAD; j += nth)
+      fdst[ch.in_dim * U + U + L * U + j] = j < ch.out_dim ? W[ch.out_dim * U + j] : 0.0f;
+  }
+  for (int e = tid; e < ch.in_dim * U + U; e += nth) fdst[e] = w[off_in + e];
+}
+
+size_t chain_mma_bytes(const mmf_chain* chain) { return image_bytes(to_dev(*chain)); }
 
 int pack_chain_mma(const mmf_chain* chain, void* dst, cudaStream_t stream) {
-  (void)chain; (void)dst; (void)stream;
-  set_error("tcgen05 operand packing is not built yet");
-  return MMF_E_UNSUPPORTED;
+  MMF_REQUIRE(chain->w != nullptr, "pack_chain_mma: chain has no fp32 weights");
+  MMF_REQUIRE(((uintptr_t)dst & 15) == 0, "pack_chain_mma: destination must be 16-byte aligned");
+  k_pack_chain_mma<<<32, 256, 0, stream>>>(to_dev(*chain), static_cast<uint8_t*>(dst));
+  MMF_LAUNCH_CHECK("k_pack_chain_mma");
+  return MMF_OK;
 }
 
-int launch_particle_chain_tc(const mmf_pf_model*, int, int, const float*, const float*, const float*, const float*,
-                             const float*, uint32_t, int, float*, float*, float*, cudaStream_t) {
-  set_error("the tcgen05 particle chain is not built yet; use MMF_PREC_FP32");
-  return MMF_E_UNSUPPORTED;
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// try_wait suspends in hardware for a bounded time; the spin bound turns a lost arrival into a trap
+// (a CUDA error the host sees) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+// start address >> 4 | LBO (16 B) << 16 | SBO (8 rows x 128 B = 1024 B) << 32 | version << 46 | layout 2 << 61
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct TcParams {
+  ChainDev chains[1 + MMF_MAX_HEADS];
+  const uint8_t* images[1 + MMF_MAX_HEADS];
+  int K;
+  uint32_t enabled;
+  int sd, N, M, single_pass;
+  long long total;
+  size_t image_cap;  // bytes reserved for the resident image (1024-aligned)
+  const float* states_in;
+  const float* eps;
+  const float* rowbias;
+  const float* logw_in;
+  const float* modw;
+  float* states_out;
+  float* logw_out;
+  float* ll_out;
+  float q[MMF_MAX_SD * MMF_MAX_SD];
+};
+
+// split 16 fp32 values into bf16 hi / lo halves and store them as the next A operand (columns
+// [8*chunk, 8*chunk+8) of the hi and lo regions)
+__device__ __forceinline__ void store_a_chunk(const float (&v)[16], uint32_t tAhi, uint32_t tAlo, int chunk,
+                                              bool single_pass) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float v0 = v[2 * j], v1 = v[2 * j + 1];
+    const uint32_t h = pack_bf16x2(v0, v1);
+    hi[j] = h;
+    const float r0 = v0 - __uint_as_float(h << 16);
+    const float r1 = v1 - __uint_as_float(h & 0xffff0000u);
+    lo[j] = pack_bf16x2(r0, r1);
+  }
+  tmem_st8(tAhi + chunk * 8, hi);
+  if (!single_pass) tmem_st8(tAlo + chunk * 8, lo);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + P.image_cap);
+  uint64_t* gbar = wbar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbar + TC_GROUPS);
+
+  const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, warp = tid >> 5;
+  const int sd = P.sd;
+  const bool single_pass = P.single_pass != 0;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int i = 0; i < TC_GROUPS; ++i) mbar_init(gbar + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t grp_cols = tmem_base + g * 128;                // lane 0 view (for the MMA issuer)
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;   // this warp's 32-lane quadrant
+  const uint32_t tD = grp_cols + lane_off;
+  const uint32_t tAhi = tD + 64, tAlo = tD + 96;
+  uint32_t wphase = 0, gphase = 0;
+
+  const long long tiles = (P.total + 127) / 128;
+  constexpr uint32_t IDESC64 = make_idesc(64), IDESC16 = make_idesc(OUT_PAD);
+
+  for (int c = 0; c <= P.K; ++c) {
+    if (c > 0 && !((P.enabled >> (c - 1)) & 1u)) continue;
+    const ChainDev ch = P.chains[c];
+    const int L = chain_layers(ch);
+    // is this the last enabled head?  (decides whether logw_out holds a running value or the result)
+    bool last_head = false, first_head = false;
+    if (c > 0) {
+      last_head = (P.enabled >> c) == 0;
+      first_head = (P.enabled & ((1u << (c - 1)) - 1u)) == 0;
+    }
+
+    // ---- bring this chain's image into shared memory (TMA bulk copy) -------------------------------
+    __syncthreads();  // every group is done with the previous image
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)image_bytes(ch);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(wbar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768) {
+        const uint32_t n = bytes - off < 32768 ? bytes - off : 32768;
+        bulk_g2s(smem + off, P.images[c] + off, n, wbar);
+      }
+    }
+    mbar_wait(wbar, wphase);
+    wphase ^= 1;
+
+    const uint32_t tiles_addr = smem_u32(smem);
+    const float* fsm = reinterpret_cast<const float*>(smem + image_tiles_bytes(ch));
+    const float* in_Wt = fsm;
+    const float* in_b = fsm + ch.in_dim * U;
+    const float* biases = in_b + U;
+    const float* out_b = biases + L * U;
+    const int mid_at = 2 * ch.n_pre;
+
+    for (long long tile = (long long)blockIdx.x * TC_GROUPS + g; tile < tiles; tile += (long long)gridDim.x * TC_GROUPS) {
+      const long long p_raw = tile * 128 + gt;
+      const bool live = p_raw < P.total;
+      const long long p = live ? p_raw : P.total - 1;
+      const int n = (int)(p / P.M);
+      const float* xsrc = (c == 0) ? P.states_in : P.states_out;
+      float x[MMF_MAX_SD];
+#pragma unroll
+      for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
+
+      // ---- input layer on the CUDA cores: xr = relu(in_W x + in_b) -> A operand ------------------------
+      float xr[U];
+#pragma unroll
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = chunk * 16 + j;
+          float a = in_b[col];
+#pragma unroll
+          for (int i = 0; i < MMF_MAX_SD; ++i)
+            if (i < sd) a = fmaf(in_Wt[i * U + col], x[i], a);
+          a = fmaxf(a, 0.0f);
+          v[j] = a;
+          xr[col] = a;
+        }
+        store_a_chunk(v, tAhi, tAlo, chunk, single_pass);
+      }
+
+      // ---- 64x64 layers ----------------------------------------------------------------------------------
+      for (int layer = 0; layer <= L; ++layer) {
+        const bool is_out = (layer == L);
+        // hand the A operand to the tensor core
+        tc_wait_st();
+        tc_fence_before();
+        group_bar(1 + g);
+        if (gt == 0) {
+          tc_fence_after();
+          const uint32_t hi_addr = tiles_addr + (is_out ? (uint32_t)L * 2 * TILE_B : (uint32_t)layer * 2 * TILE_B);
+          const uint32_t lo_addr = hi_addr + (is_out ? OUT_TILE_B : TILE_B);
+          const uint64_t bhi = make_b_desc(hi_addr), blo = make_b_desc(lo_addr);
+          const uint32_t idesc = is_out ? IDESC16 : IDESC64;
+          const uint32_t a_hi = grp_cols + 64, a_lo = grp_cols + 96;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ts(grp_cols, a_hi + k * 8, bhi + (uint64_t)(k * 2), idesc, k > 0);
+          if (!single_pass) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ts(grp_cols, a_hi + k * 8, blo + (uint64_t)(k * 2), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ts(grp_cols, a_lo + k * 8, bhi + (uint64_t)(k * 2), idesc, 1);
+          }
+          tc_commit(gbar + g);
+        }
+        mbar_wait(gbar + g, gphase);
+        gphase ^= 1;
+        tc_fence_after();
+        if (is_out) break;
+
+        // ---- epilogue of this layer = producer of the next layer's A operand ---------------------------
+        const bool is_mid = (layer == mid_at);
+        const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
+        const bool res_a = !is_mid && ((rel & 1) == 0);  // first half of a resblock: keep xr
+        const bool res_b = !is_mid && ((rel & 1) == 1);  // second half: add xr
+        const float resid_scale = res_b ? 1.0f : 0.0f;
+        const float floor_v = (is_mid && !ch.mid_relu) ? -INFINITY : 0.0f;
+        const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U);
+        const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          uint32_t d[16];
+          tmem_ld16(tD + chunk * 16, d);
+          float bias[16];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 b = is_mid ? __ldg(brow + chunk * 4 + q4) : bsm[chunk * 4 + q4];
+            bias[4 * q4 + 0] = b.x; bias[4 * q4 + 1] = b.y; bias[4 * q4 + 2] = b.z; bias[4 * q4 + 3] = b.w;
+          }
+          tc_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = chunk * 16 + j;
+            float a = __uint_as_float(d[j]) + bias[j];
+            a = fmaf(resid_scale, xr[col], a);
+            a = fmaxf(a, floor_v);
+            v[j] = a;
+            xr[col] = res_a ? xr[col] : a;
+          }
+          store_a_chunk(v, tAhi, tAlo, chunk, single_pass);
+        }
+      }
+
+      // ---- output layer result: y[o] = D[o] + out_b[o] -----------------------------------------------------
+      float y[MMF_MAX_SD + 1];
+      {
+        uint32_t d[16];
+        tmem_ld16(tD, d);
+        tc_wait_ld();
+#pragma unroll
+        for (int o = 0; o < MMF_MAX_SD + 1; ++o) y[o] = __uint_as_float(d[o]) + out_b[o];
+      }
+
+      if (c == 0) {
+        float gsel = 0.0f;
+#pragma unroll
+        for (int o = 0; o < MMF_MAX_SD + 1; ++o)
+          if (o == sd) gsel = y[o];
+        const float gate = 1.0f / (1.0f + expf(-gsel));
+        float e[MMF_MAX_SD];
+#pragma unroll
+        for (int i = 0; i < MMF_MAX_SD; ++i) e[i] = (i < sd) ? P.eps[p * sd + i] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < MMF_MAX_SD; ++i) {
+          if (i < sd) {
+            float noise = 0.0f;
+#pragma unroll
+            for (int j = 0; j < MMF_MAX_SD; ++j)
+              if (j <= i && j < sd) noise = fmaf(P.q[i * sd + j], e[j], noise);
+            const float moved = (x[i] + y[i] * gate) + noise;
+            if (live) P.states_out[p * sd + i] = moved;
+          }
+        }
+      } else {
+        const float ll = y[0];
+        if (P.ll_out != nullptr && live) P.ll_out[(size_t)(c - 1) * P.total + p] = ll;
+        const float v = ll + (P.modw != nullptr ? __ldg(P.modw + (size_t)n * P.K + (c - 1)) : 0.0f);
+        float fused = v;
+        if (!first_head) {  // running log-sum-exp kept in logw_out between head phases
+          const float prev = P.logw_out[p];
+          const float mx = fmaxf(prev, v);
+          fused = (mx == -INFINITY) ? -INFINITY : mx + logf(expf(prev - mx) + expf(v - mx));
+        }
+        if (live) P.logw_out[p] = last_head ? P.logw_in[p] + fused : fused;
+      }
+      // the next tile's input layer overwrites the A region: the out-layer MMA that read it has completed
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
+                             const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
+                             int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream) {
+  TcParams P;
+  P.K = model->num_heads;
+  size_t cap = 0;
+  for (int c = 0; c <= P.K; ++c) {
+    const mmf_chain& src = (c == 0) ? model->dynamics : model->heads[c - 1];
+    P.chains[c] = to_dev(src);
+    P.images[c] = static_cast<const uint8_t*>(src.w_mma);
+    if (c == 0 || ((enabled >> (c - 1)) & 1u)) {
+      MMF_REQUIRE(src.w_mma != nullptr, "tensor-core chain %d has no operand image: call mmf_pack_chain_mma first", c);
+      MMF_REQUIRE(((uintptr_t)src.w_mma & 15) == 0, "operand image %d must be 16-byte aligned", c);
+      const size_t b = image_bytes(P.chains[c]);
+      cap = b > cap ? b : cap;
+    }
+  }
+  cap = (cap + 1023) & ~(size_t)1023;
+  P.image_cap = cap;
+  P.enabled = enabled;
+  P.sd = model->state_dim;
+  P.N = N;
+  P.M = M;
+  P.single_pass = (precision == MMF_PREC_BF16) ? 1 : 0;
+  P.total = (long long)N * M;
+  P.states_in = states_in;
+  P.eps = eps;
+  P.rowbias = rowbias;
+  P.logw_in = logw_in;
+  P.modw = modw;
+  P.states_out = states_out;
+  P.logw_out = logw_out;
+  P.ll_out = ll_out;
+  for (int i = 0; i < MMF_MAX_SD * MMF_MAX_SD; ++i) P.q[i] = model->q_tril[i];
+
+  const size_t smem = cap + 1024;  // + barriers, TMEM slot (and slack for the 1024-byte alignment)
+  static thread_local int configured_dev = -1;
+  static thread_local size_t window = 0;
+  int dev = 0;
+  MMF_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    int rc = opt_in_shared_memory(k_particle_chain_tc, &window);
+    if (rc) return rc;
+    configured_dev = dev;
+  }
+  MMF_REQUIRE(smem <= window, "tensor-core chain needs %zu B of shared memory (window %zu B)", smem, window);
+  int sms = 148;
+  MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = (P.total + 127) / 128;
+  long long grid = (tiles + TC_GROUPS - 1) / TC_GROUPS;
+  if (grid > sms) grid = sms;
+  k_particle_chain_tc<<<(int)grid, TC_THREADS, smem, stream>>>(P);
+  MMF_LAUNCH_CHECK("k_particle_chain_tc");
+  return MMF_OK;
 }
 
 }  // namespace mmf

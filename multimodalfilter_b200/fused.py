@@ -272,6 +272,10 @@ class PFPlan:
         q = self.dyn.q()
         for i in range(_lib.MAX_SD * _lib.MAX_SD):
             m.q_tril[i] = float(q[i])
+        # tcgen05 operand images (bf16 hi/lo halves in the UMMA shared-memory layout)
+        bufs.append(ops.pack_chain_mma(m.dynamics, device))
+        for k in range(self.K):
+            bufs.append(ops.pack_chain_mma(m.heads[k], device))
         self._buffers, self.struct, self._sig = bufs, m, sig
 
     # -- per-trajectory inputs ------------------------------------------------------------------------

@@ -77,6 +77,17 @@ def is_systematic(mode: int) -> bool:
     return mode in (RESAMPLE_SYSTEMATIC_STRICT, RESAMPLE_SYSTEMATIC_FAST)
 
 
+def pack_chain_mma(chain_struct, device):
+    """Build the tensor-core operand image of a chain in place: allocates the buffer, runs the pack
+    kernel, stores the pointer in ``chain_struct.w_mma`` and returns the buffer (keep it alive)."""
+    lib = _lib.load()
+    nbytes = lib.mmf_chain_mma_bytes(C.byref(chain_struct))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    _lib.check(lib.mmf_pack_chain_mma(C.byref(chain_struct), _lib.ptr(buf), _lib.stream_of(buf)))
+    chain_struct.w_mma = buf.data_ptr()
+    return buf
+
+
 def pf_init(mean, covariance, eps_MNsd):
     """R2: (N,sd), (N,sd,sd), (M,N,sd) -> particle_states (N,M,sd), particle_log_weights (N,M)."""
     lib = _lib.load()

@@ -189,7 +189,8 @@ def test_normalize_estimate_resample(mode, N, M, sd, M_out, alpha, estimation):
     ("PushParticleFilter", 2, None),
 ])
 @pytest.mark.parametrize("N,Mp", [(5, 30), (3, 300), (2, 1000)])
-def test_predict_measure_matches_oracle_modules(name, sd, flags, N, Mp):
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_predict_measure_matches_oracle_modules(name, sd, flags, N, Mp, precision):
     oracle_f = fill_parameters(getattr(port, name)(), seed=21).eval()
     prod_f = fill_parameters(_product(name)(), seed=21).to(DEV).eval()
     if flags is not None:
@@ -218,7 +219,11 @@ def test_predict_measure_matches_oracle_modules(name, sd, flags, N, Mp):
         modw = plan.modality_log_weights(obs_d)
     rowbias = ops.pf_traj_rows(plan.struct, plan.K, u0.to(DEV), feats)
     moved_k, logw_k, ll_k = ops.pf_predict_measure(plan.struct, states.to(DEV), eps.to(DEV), rowbias, logw.to(DEV),
-                                                   modw, plan.enabled_mask(), precision=ops.PREC_FP32, want_ll=True)
+                                                   modw, plan.enabled_mask(), precision=ops.PRECISIONS[precision],
+                                                   want_ll=True)
+    # fp32 (CUDA cores) and bf16x3 (tcgen05, split operands) are parity grade; single-pass bf16 is the
+    # opt-in fast mode and is only held to bf16 accuracy (8 mantissa bits through ~10 layers)
+    RTOL = 1e-4 if precision != "bf16" else 3e-2
     assert_close(moved_k.cpu(), moved, RTOL, msg="moved particle states")
     assert_close(logw_k.cpu(), ref_logw, RTOL, msg="un-normalised log-weights")
     # per-head log-likelihoods against the oracle's individual heads
