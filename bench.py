@@ -197,7 +197,7 @@ def main():
     task = "push" if name.startswith("Push") else "door"
     filt = fill_parameters(M_.MODEL_TYPES[task][name](), seed=0).to(dev).eval()
     is_pf = hasattr(filt, "num_particles")
-    precision = args.precision or "fp32"
+    precision = args.precision or "bf16x3"
     if is_pf:
         filt.num_particles = Mp
         filt.precision = precision

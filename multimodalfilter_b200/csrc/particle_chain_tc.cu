@@ -227,22 +227,59 @@ struct TcParams {
   float q[MMF_MAX_SD * MMF_MAX_SD];
 };
 
-// split 16 fp32 values into bf16 hi / lo halves and store them as the next A operand (columns
-// [8*chunk, 8*chunk+8) of the hi and lo regions)
-__device__ __forceinline__ void store_a_chunk(const float (&v)[16], uint32_t tAhi, uint32_t tAlo, int chunk,
+// split 8 fp32 pairs into bf16 hi / lo halves and store them as the next A operand (columns
+// [8*chunk, 8*chunk+8) of the hi and lo regions).  5 instructions per pair: F2FP, SHL, LOP, FFMA2, F2FP.
+__device__ __forceinline__ void store_a_chunk(const float2 (&v)[8], uint32_t tAhi, uint32_t tAlo, int chunk,
                                               bool single_pass) {
   uint32_t hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float v0 = v[2 * j], v1 = v[2 * j + 1];
-    const uint32_t h = pack_bf16x2(v0, v1);
+    const uint32_t h = pack_bf16x2(v[j].x, v[j].y);
     hi[j] = h;
-    const float r0 = v0 - __uint_as_float(h << 16);
-    const float r1 = v1 - __uint_as_float(h & 0xffff0000u);
-    lo[j] = pack_bf16x2(r0, r1);
+    const float2 hf = make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u));
+    const float2 r = __ffma2_rn(hf, make_float2(-1.0f, -1.0f), v[j]);
+    lo[j] = pack_bf16x2(r.x, r.y);
   }
   tmem_st8(tAhi + chunk * 8, hi);
   if (!single_pass) tmem_st8(tAlo + chunk * 8, lo);
+}
+
+enum { EPI_RES_A = 0, EPI_RES_B = 1, EPI_MID_RELU = 2, EPI_MID_LINEAR = 3 };
+
+// Epilogue of one 64-wide layer for this thread's row: accumulator (TMEM) -> +bias (+residual) ->
+// activation -> residual stream update -> bf16 split -> next A operand (TMEM).
+//   RES_A : t = relu(D + b1)          residual stream xr untouched
+//   RES_B : y = relu(D + b2 + xr)     xr = y
+//   MID_* : v = [relu](D + rowbias)   xr = v      (bias4 then points at the per-trajectory row in global memory)
+template <int KIND>
+__device__ __forceinline__ void epilogue(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float4* __restrict__ bias4,
+                                         float2 (&xr)[U / 2], bool single_pass) {
+#pragma unroll
+  for (int chunk = 0; chunk < 4; ++chunk) {
+    uint32_t d[16];
+    tmem_ld16(tD + chunk * 16, d);
+    float2 b[8];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 t = (KIND >= EPI_MID_RELU) ? __ldg(bias4 + chunk * 4 + q4) : bias4[chunk * 4 + q4];
+      b[2 * q4] = make_float2(t.x, t.y);
+      b[2 * q4 + 1] = make_float2(t.z, t.w);
+    }
+    tc_wait_ld();
+    float2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 a = __fadd2_rn(make_float2(__uint_as_float(d[2 * j]), __uint_as_float(d[2 * j + 1])), b[j]);
+      if (KIND == EPI_RES_B) a = __fadd2_rn(a, xr[chunk * 8 + j]);
+      if (KIND != EPI_MID_LINEAR) {
+        a.x = fmaxf(a.x, 0.0f);
+        a.y = fmaxf(a.y, 0.0f);
+      }
+      if (KIND != EPI_RES_A) xr[chunk * 8 + j] = a;
+      v[j] = a;
+    }
+    store_a_chunk(v, tAhi, tAlo, chunk, single_pass);
+  }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __grid_constant__ TcParams P) {
@@ -322,22 +359,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __gri
       for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
 
       // ---- input layer on the CUDA cores: xr = relu(in_W x + in_b) -> A operand ------------------------
-      float xr[U];
+      float2 xr[U / 2];
+      {
+        const float4* b4 = reinterpret_cast<const float4*>(in_b);
+        const float4* w4 = reinterpret_cast<const float4*>(in_Wt);
 #pragma unroll
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        float v[16];
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          float2 v[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = chunk * 16 + j;
-          float a = in_b[col];
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 t = b4[chunk * 4 + q4];
+            v[2 * q4] = make_float2(t.x, t.y);
+            v[2 * q4 + 1] = make_float2(t.z, t.w);
+          }
 #pragma unroll
-          for (int i = 0; i < MMF_MAX_SD; ++i)
-            if (i < sd) a = fmaf(in_Wt[i * U + col], x[i], a);
-          a = fmaxf(a, 0.0f);
-          v[j] = a;
-          xr[col] = a;
+          for (int i = 0; i < MMF_MAX_SD; ++i) {
+            if (i < sd) {
+              const float2 xi = make_float2(x[i], x[i]);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 t = w4[i * (U / 4) + chunk * 4 + q4];
+                v[2 * q4] = __ffma2_rn(make_float2(t.x, t.y), xi, v[2 * q4]);
+                v[2 * q4 + 1] = __ffma2_rn(make_float2(t.z, t.w), xi, v[2 * q4 + 1]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j].x = fmaxf(v[j].x, 0.0f);
+            v[j].y = fmaxf(v[j].y, 0.0f);
+            xr[chunk * 8 + j] = v[j];
+          }
+          store_a_chunk(v, tAhi, tAlo, chunk, single_pass);
         }
-        store_a_chunk(v, tAhi, tAlo, chunk, single_pass);
       }
 
       // ---- 64x64 layers ----------------------------------------------------------------------------------
@@ -370,36 +424,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __gri
         if (is_out) break;
 
         // ---- epilogue of this layer = producer of the next layer's A operand ---------------------------
-        const bool is_mid = (layer == mid_at);
-        const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
-        const bool res_a = !is_mid && ((rel & 1) == 0);  // first half of a resblock: keep xr
-        const bool res_b = !is_mid && ((rel & 1) == 1);  // second half: add xr
-        const float resid_scale = res_b ? 1.0f : 0.0f;
-        const float floor_v = (is_mid && !ch.mid_relu) ? -INFINITY : 0.0f;
-        const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U);
-        const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
-#pragma unroll
-        for (int chunk = 0; chunk < 4; ++chunk) {
-          uint32_t d[16];
-          tmem_ld16(tD + chunk * 16, d);
-          float bias[16];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 b = is_mid ? __ldg(brow + chunk * 4 + q4) : bsm[chunk * 4 + q4];
-            bias[4 * q4 + 0] = b.x; bias[4 * q4 + 1] = b.y; bias[4 * q4 + 2] = b.z; bias[4 * q4 + 3] = b.w;
-          }
-          tc_wait_ld();
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = chunk * 16 + j;
-            float a = __uint_as_float(d[j]) + bias[j];
-            a = fmaf(resid_scale, xr[col], a);
-            a = fmaxf(a, floor_v);
-            v[j] = a;
-            xr[col] = res_a ? xr[col] : a;
-          }
-          store_a_chunk(v, tAhi, tAlo, chunk, single_pass);
+        if (layer == mid_at) {
+          const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
+          if (ch.mid_relu) epilogue<EPI_MID_RELU>(tD, tAhi, tAlo, brow, xr, single_pass);
+          else epilogue<EPI_MID_LINEAR>(tD, tAhi, tAlo, brow, xr, single_pass);
+        } else {
+          const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
+          const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U);
+          if ((rel & 1) == 0) epilogue<EPI_RES_A>(tD, tAhi, tAlo, bsm, xr, single_pass);
+          else epilogue<EPI_RES_B>(tD, tAhi, tAlo, bsm, xr, single_pass);
         }
       }
 

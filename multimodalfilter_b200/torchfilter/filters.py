@@ -76,7 +76,7 @@ class ParticleFilter(Filter):
         # extensions
         self.noise = None
         self.resample_mode = "multinomial"
-        self.precision = "fp32"
+        self.precision = "bf16x3"
         self.debug = None  # set to a dict to capture intermediates of the last fused step
 
     # ---- plan management -------------------------------------------------------------------------
