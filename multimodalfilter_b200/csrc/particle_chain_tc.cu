@@ -23,13 +23,16 @@
 //
 // Replaces the same reference lines as particle_chain_ffma.cu.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
 namespace mmf {
 
-constexpr int TC_GROUPS = 4;
-constexpr int TC_THREADS = TC_GROUPS * 128;
+// GROUPS independent tile pipelines per CTA; TPR threads share one particle row (each owns 64/TPR
+// activation columns), so a group is 128*TPR threads = 4*TPR warps, all four TMEM lane quadrants
+// covered TPR times.  TMEM: 128 columns per group (64 accumulator + 32 A_hi + 32 A_lo) => GROUPS <= 4.
+constexpr int TC_MAX_GROUPS = 4;
 constexpr int TILE_B = 64 * 128;      // one 64(N) x 64(K) bf16 operand tile: 64 rows of 128 bytes
 constexpr int OUT_TILE_B = 16 * 128;  // the output layer, N padded to 16
 constexpr int OUT_PAD = 16;
@@ -135,24 +138,24 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)  // suspend-time hint (ns): park instead of spinning
       : "memory");
   return ok != 0;
 }
 // try_wait suspends in hardware for a bounded time; the spin bound turns a lost arrival into a trap
 // (a CUDA error the host sees) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 0) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait(bar, parity, hint_ns)) {
     if (++spins > (1u << 24)) __trap();
   }
 }
@@ -170,7 +173,9 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void group_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // D[tmem] (+)= A[tmem] * B[smem desc]^T, bf16 x bf16 -> fp32
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
@@ -214,6 +219,7 @@ struct TcParams {
   int K;
   uint32_t enabled;
   int sd, N, M, single_pass;
+  uint32_t wait_hint_ns;
   long long total;
   size_t image_cap;  // bytes reserved for the resident image (1024-aligned)
   const float* states_in;
@@ -251,11 +257,12 @@ enum { EPI_RES_A = 0, EPI_RES_B = 1, EPI_MID_RELU = 2, EPI_MID_LINEAR = 3 };
 //   RES_A : t = relu(D + b1)          residual stream xr untouched
 //   RES_B : y = relu(D + b2 + xr)     xr = y
 //   MID_* : v = [relu](D + rowbias)   xr = v      (bias4 then points at the per-trajectory row in global memory)
-template <int KIND>
+// tD / tAhi / tAlo / bias4 already point at this thread's first column.
+template <int KIND, int COLS>
 __device__ __forceinline__ void epilogue(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float4* __restrict__ bias4,
-                                         float2 (&xr)[U / 2], bool single_pass) {
+                                         float2 (&xr)[COLS / 2], bool single_pass) {
 #pragma unroll
-  for (int chunk = 0; chunk < 4; ++chunk) {
+  for (int chunk = 0; chunk < COLS / 16; ++chunk) {
     uint32_t d[16];
     tmem_ld16(tD + chunk * 16, d);
     float2 b[8];
@@ -282,13 +289,19 @@ __device__ __forceinline__ void epilogue(uint32_t tD, uint32_t tAhi, uint32_t tA
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __grid_constant__ TcParams P) {
+template <int TC_GROUPS, int TC_TPR>
+__global__ void __launch_bounds__(TC_GROUPS * 128 * TC_TPR, 1) k_particle_chain_tc(const __grid_constant__ TcParams P) {
+  constexpr int TC_GROUP_THREADS = 128 * TC_TPR;
+  constexpr int TC_COLS = U / TC_TPR;  // activation columns owned by one thread
+  constexpr int TC_CHUNKS = TC_COLS / 16;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + P.image_cap);
   uint64_t* gbar = wbar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbar + TC_GROUPS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbar + TC_MAX_GROUPS);
 
-  const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, warp = tid >> 5;
+  const int tid = threadIdx.x, g = tid / TC_GROUP_THREADS, gt = tid % TC_GROUP_THREADS, warp = tid >> 5;
+  const int row = gt & 127;        // particle row inside the tile == TMEM lane
+  const int col0 = (gt >> 7) * TC_COLS;  // first activation column owned by this thread
   const int sd = P.sd;
   const bool single_pass = P.single_pass != 0;
 
@@ -308,8 +321,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __gri
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t grp_cols = tmem_base + g * 128;                // lane 0 view (for the MMA issuer)
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;   // this warp's 32-lane quadrant
-  const uint32_t tD = grp_cols + lane_off;
-  const uint32_t tAhi = tD + 64, tAlo = tD + 96;
+  const uint32_t tD0 = grp_cols + lane_off;             // accumulator, column 0 (output layer)
+  const uint32_t tD = tD0 + col0;                       // this thread's accumulator columns
+  const uint32_t tAhi = tD0 + 64 + col0 / 2, tAlo = tD0 + 96 + col0 / 2;
   uint32_t wphase = 0, gphase = 0;
 
   const long long tiles = (P.total + 127) / 128;
@@ -349,7 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __gri
     const int mid_at = 2 * ch.n_pre;
 
     for (long long tile = (long long)blockIdx.x * TC_GROUPS + g; tile < tiles; tile += (long long)gridDim.x * TC_GROUPS) {
-      const long long p_raw = tile * 128 + gt;
+      const long long p_raw = tile * 128 + row;
       const bool live = p_raw < P.total;
       const long long p = live ? p_raw : P.total - 1;
       const int n = (int)(p / P.M);
@@ -359,12 +373,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __gri
       for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
 
       // ---- input layer on the CUDA cores: xr = relu(in_W x + in_b) -> A operand ------------------------
-      float2 xr[U / 2];
+      float2 xr[TC_COLS / 2];
       {
-        const float4* b4 = reinterpret_cast<const float4*>(in_b);
-        const float4* w4 = reinterpret_cast<const float4*>(in_Wt);
+        const float4* b4 = reinterpret_cast<const float4*>(in_b + col0);
+        const float4* w4 = reinterpret_cast<const float4*>(in_Wt + col0);
 #pragma unroll
-        for (int chunk = 0; chunk < 4; ++chunk) {
+        for (int chunk = 0; chunk < TC_CHUNKS; ++chunk) {
           float2 v[8];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __gri
         // hand the A operand to the tensor core
         tc_wait_st();
         tc_fence_before();
-        group_bar(1 + g);
+        group_bar(1 + g, TC_GROUP_THREADS);
         if (gt == 0) {
           tc_fence_after();
           const uint32_t hi_addr = tiles_addr + (is_out ? (uint32_t)L * 2 * TILE_B : (uint32_t)layer * 2 * TILE_B);
@@ -418,29 +432,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_particle_chain_tc(const __gri
           }
           tc_commit(gbar + g);
         }
-        mbar_wait(gbar + g, gphase);
+        mbar_wait(gbar + g, gphase, P.wait_hint_ns);
         gphase ^= 1;
         tc_fence_after();
         if (is_out) break;
 
         // ---- epilogue of this layer = producer of the next layer's A operand ---------------------------
         if (layer == mid_at) {
-          const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
-          if (ch.mid_relu) epilogue<EPI_MID_RELU>(tD, tAhi, tAlo, brow, xr, single_pass);
-          else epilogue<EPI_MID_LINEAR>(tD, tAhi, tAlo, brow, xr, single_pass);
+          const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U + col0);
+          if (ch.mid_relu) epilogue<EPI_MID_RELU, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass);
+          else epilogue<EPI_MID_LINEAR, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass);
         } else {
           const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
-          const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U);
-          if ((rel & 1) == 0) epilogue<EPI_RES_A>(tD, tAhi, tAlo, bsm, xr, single_pass);
-          else epilogue<EPI_RES_B>(tD, tAhi, tAlo, bsm, xr, single_pass);
+          const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U + col0);
+          if ((rel & 1) == 0) epilogue<EPI_RES_A, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass);
+          else epilogue<EPI_RES_B, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass);
         }
       }
 
       // ---- output layer result: y[o] = D[o] + out_b[o] -----------------------------------------------------
+      if (col0 != 0) continue;  // the row's other threads are done (warp-uniform: col0 is per warp)
       float y[MMF_MAX_SD + 1];
       {
         uint32_t d[16];
-        tmem_ld16(tD, d);
+        tmem_ld16(tD0, d);
         tc_wait_ld();
 #pragma unroll
         for (int o = 0; o < MMF_MAX_SD + 1; ++o) y[o] = __uint_as_float(d[o]) + out_b[o];
@@ -525,22 +540,39 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
   for (int i = 0; i < MMF_MAX_SD * MMF_MAX_SD; ++i) P.q[i] = model->q_tril[i];
 
   const size_t smem = cap + 1024;  // + barriers, TMEM slot (and slack for the 1024-byte alignment)
-  static thread_local int configured_dev = -1;
-  static thread_local size_t window = 0;
-  int dev = 0;
+  // pipeline shape: MMF_TC_VARIANT=<groups><threads-per-row>, e.g. 41 (default), 32, 42, 31, 22
+  int variant = 41;
+  if (const char* env = getenv("MMF_TC_VARIANT")) variant = atoi(env);
+  P.wait_hint_ns = 0;
+  if (const char* env = getenv("MMF_TC_WAIT_HINT_NS")) P.wait_hint_ns = (uint32_t)atoi(env);
+  int sms = 148, dev = 0;
   MMF_CUDA(cudaGetDevice(&dev));
-  if (configured_dev != dev) {
-    int rc = opt_in_shared_memory(k_particle_chain_tc, &window);
-    if (rc) return rc;
-    configured_dev = dev;
-  }
-  MMF_REQUIRE(smem <= window, "tensor-core chain needs %zu B of shared memory (window %zu B)", smem, window);
-  int sms = 148;
   MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long tiles = (P.total + 127) / 128;
-  long long grid = (tiles + TC_GROUPS - 1) / TC_GROUPS;
-  if (grid > sms) grid = sms;
-  k_particle_chain_tc<<<(int)grid, TC_THREADS, smem, stream>>>(P);
+#define MMF_TC_LAUNCH(G, T)                                                                   \
+  do {                                                                                        \
+    static thread_local int configured_dev = -1;                                              \
+    static thread_local size_t window = 0;                                                    \
+    if (configured_dev != dev) {                                                              \
+      int rc = opt_in_shared_memory(k_particle_chain_tc<G, T>, &window);                      \
+      if (rc) return rc;                                                                      \
+      configured_dev = dev;                                                                   \
+    }                                                                                         \
+    MMF_REQUIRE(smem <= window, "tensor-core chain needs %zu B of shared memory (window %zu B)", smem, window); \
+    long long grid = (tiles + G - 1) / G;                                                     \
+    if (grid > sms) grid = sms;                                                               \
+    k_particle_chain_tc<G, T><<<(int)grid, G * 128 * T, smem, stream>>>(P);                   \
+  } while (0)
+  switch (variant) {
+    case 41: MMF_TC_LAUNCH(4, 1); break;
+    case 31: MMF_TC_LAUNCH(3, 1); break;
+    case 21: MMF_TC_LAUNCH(2, 1); break;
+    case 32: MMF_TC_LAUNCH(3, 2); break;
+    case 42: MMF_TC_LAUNCH(4, 2); break;
+    case 22: MMF_TC_LAUNCH(2, 2); break;
+    default: set_error("unknown MMF_TC_VARIANT %d", variant); return MMF_E_INVALID;
+  }
+#undef MMF_TC_LAUNCH
   MMF_LAUNCH_CHECK("k_particle_chain_tc");
   return MMF_OK;
 }

@@ -1,0 +1,115 @@
+// Microbenchmark: TMEM load/store throughput, TS-form UMMA rate, and whether they overlap (B200).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+               "r"(a), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+        "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+        "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+        "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t a) {
+  return (uint64_t)((a >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
+
+
+template <int N, int NACC>
+__global__ void __launch_bounds__(128, 1) mma_rate(int batches, int reps, unsigned long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot;
+  if (tid == 0) {
+    const uint64_t b0 = make_b_desc(smem_u32(smem));
+    const uint32_t id = idesc(N);
+    uint32_t phase = 0;
+    const unsigned long long t0 = clock64();
+    for (int it = 0; it < batches; ++it) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+          mma_ts(base + (k % NACC) * (N > 128 ? 256 : 128), base + 480 + (k & 3) * 8, b0 + (uint64_t)((k & 3) * 2), id, 1);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(&bar)), "r"(phase)
+                     : "memory");
+      }
+      phase ^= 1;
+    }
+    out[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512) : "memory");
+}
+
+template <int N, int NACC>
+void run_rate(unsigned long long* out) {
+  cudaFuncSetAttribute(mma_rate<N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  for (int reps : {1, 4, 16}) {
+    out[0] = 0;
+    mma_rate<N, NACC><<<1, 128, 65536>>>(100, reps, out);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s\n", cudaGetErrorString(e)); exit(1); }
+    printf("N=%3d accumulators=%d mmas/commit=%3d : %7llu cyc per batch, %6.1f cyc per MMA\n", N, NACC, 12 * reps, out[0] / 100,
+           (double)out[0] / (100.0 * 12 * reps));
+  }
+}
+
+int main() {
+  unsigned long long* out;
+  cudaMallocManaged(&out, 64);
+  run_rate<16, 1>(out);
+  run_rate<64, 1>(out);
+  run_rate<64, 2>(out);
+  run_rate<64, 4>(out);
+  run_rate<128, 1>(out);
+  run_rate<128, 2>(out);
+  run_rate<256, 1>(out);
+  return 0;
+}
