@@ -429,3 +429,40 @@ def test_full_size_step_properties_and_shard_invariance():
     assert torch.equal(torch.cat([a[1], b[1]]), lw)
     for key in ("states", "estimate", "idx", "logw_norm"):
         assert torch.equal(torch.cat([a[2][key], b[2][key]]), out[key]), key
+
+
+# ---- training path: gradients through the recursion (BPTT, BASELINE config C4 in miniature) ---------
+def test_bptt_gradients_match_oracle():
+    """PushCrossmodalParticleFilter.train(): no resampling, MSE on the estimates, backward through all steps.
+    Gradients of the measurement / weight-model parameters (the ones the reference's curricula train; the
+    dynamics is frozen there, ref: scripts/push_task/train_push.py:154) and of the dynamics parameters
+    must match the CPU oracle's autograd."""
+    name, sd, N, Mp, T = "PushCrossmodalParticleFilter", 2, 6, 30, 5
+    init, eps, _ = draw_noise(T, N, Mp, sd, seed=13)
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=14)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd)
+    grads = []
+    for side in ("oracle", "product"):
+        if side == "oracle":
+            f = fill_parameters(getattr(port, name)(), seed=27)
+            f.noise = RecordedNoise(init_eps=init, process_eps=eps)
+            dev = "cpu"
+        else:
+            f = fill_parameters(_product(name)(), seed=27).to(DEV)
+            f.noise = ReplayNoise(init_eps=init, process_eps=eps)
+            dev = DEV
+        f.train()
+        f.num_particles = Mp
+        f.initialize_beliefs(mean=states[0].to(dev), covariance=cov.to(dev).contiguous())
+        est = f.forward_loop(observations={k: v[1:].to(dev) for k, v in obs.items()}, controls=controls[1:].to(dev))
+        loss = torch.mean((est - states[1:].to(dev)) ** 2)
+        loss.backward()
+        grads.append((loss.item(), {k: p.grad.detach().cpu() for k, p in f.named_parameters() if p.grad is not None}))
+    (lo, go), (lp, gp) = grads
+    assert abs(lo - lp) <= 1e-4 * abs(lo)
+    assert set(go) == set(gp) and len(go) > 50
+    # gradients span many orders of magnitude across the tree (the image-encoder convolutions see ~1e-7):
+    # compare each tensor relative to its own scale, with an absolute floor tied to the largest gradient
+    floor = 1e-5 * max(float(g.abs().max()) for g in go.values())
+    for k in go:
+        assert_close(gp[k], go[k], 2e-3, atol=floor, msg=f"grad {k}")

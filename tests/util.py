@@ -53,7 +53,7 @@ def assert_close(actual, expected, rtol=1e-4, atol=None, msg=""):
     assert np.array_equal(a[~finite], e[~finite], equal_nan=True), f"{msg}: inf/nan entries differ"
     if not finite.any():
         return
-    scale = np.sqrt(np.mean(e[finite] ** 2)) if atol is None else 0.0
+    scale = np.sqrt(np.mean(e[finite] ** 2))
     bound = rtol * np.maximum(np.abs(e), scale) + (atol or 0.0)
     err = np.abs(a - e)
     bad = finite & (err > bound)
