@@ -1,6 +1,3 @@
 #!/bin/bash
-for v in 41 31 21 32 42 22; do
-  for h in 0 20000; do
-    echo "variant=$v hint=$h"; MMF_TC_VARIANT=$v MMF_TC_WAIT_HINT_NS=$h timeout 120 python tools/time_step.py bf16x3 bf16 | cut -c1-75
-  done
-done
+MMF_TC_VARIANT=41 timeout -k 10 200 python -m pytest tests -m gpu -q -k "predict_measure and bf16" 2>&1 | tail -3
+MMF_TC_VARIANT=41 timeout 120 python tools/time_step.py bf16x3 bf16 | cut -c1-75
