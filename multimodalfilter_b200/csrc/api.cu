@@ -113,9 +113,8 @@ int mmf_pf_predict_measure(const mmf_pf_model* model, int32_t N, int32_t M, cons
 }
 
 size_t mmf_pf_resample_workspace_bytes(int32_t N, int32_t M) {
-  (void)N;
-  (void)M;
-  return 0;  // the shared-memory path needs none; reserved for the large-M path
+  if (N <= 0 || M <= 0) return 0;
+  return resample_workspace_bytes(N, M);
 }
 
 int mmf_pf_normalize_resample(int32_t N, int32_t M, int32_t sd, const float* states, const float* logw_unnorm,
@@ -123,7 +122,6 @@ int mmf_pf_normalize_resample(int32_t N, int32_t M, int32_t sd, const float* sta
                               int32_t M_out, const double* uniforms, float* states_out, float* logw_out,
                               float* est_out, float* logw_norm_out, float* logits_out, int64_t* idx_out,
                               void* workspace, void* stream) {
-  (void)workspace;
   MMF_REQUIRE(N >= 0 && M >= 1 && sd >= 1 && sd <= MMF_MAX_SD, "normalize_resample: bad shape N=%d M=%d sd=%d", N, M, sd);
   MMF_REQUIRE(estimation_method == MMF_ESTIMATE_WEIGHTED_AVERAGE || estimation_method == MMF_ESTIMATE_ARGMAX,
               "normalize_resample: unknown estimation method %d", estimation_method);
@@ -145,7 +143,7 @@ int mmf_pf_normalize_resample(int32_t N, int32_t M, int32_t sd, const float* sta
   P.states = states; P.logw_unnorm = logw_unnorm; P.logits_in = nullptr; P.uniforms = uniforms;
   P.states_out = states_out; P.logw_out = logw_out; P.est_out = est_out;
   P.logw_norm_out = logw_norm_out; P.logits_out = logits_out; P.idx_out = (long long*)idx_out;
-  return launch_normalize_resample(P, (cudaStream_t)stream);
+  return launch_normalize_resample(P, workspace, (cudaStream_t)stream);
 }
 
 int mmf_fuse_loglik(int32_t N, int32_t M, int32_t K, const float* ll, const float* w, float* out, void* stream) {
@@ -156,7 +154,6 @@ int mmf_fuse_loglik(int32_t N, int32_t M, int32_t K, const float* ll, const floa
 
 int mmf_resample(int32_t N, int32_t M, int32_t M_out, const float* logits, int32_t resample_mode,
                  const double* uniforms, int64_t* idx_out, void* workspace, void* stream) {
-  (void)workspace;
   MMF_REQUIRE(N >= 0 && M >= 1 && M_out >= 1, "resample: bad shape N=%d M=%d M_out=%d", N, M, M_out);
   MMF_REQUIRE(resample_mode > MMF_RESAMPLE_NONE && resample_mode <= MMF_RESAMPLE_SYSTEMATIC_FAST,
               "resample: unknown resample mode %d", resample_mode);
@@ -167,7 +164,7 @@ int mmf_resample(int32_t N, int32_t M, int32_t M_out, const float* logits, int32
   P.N = N; P.M = M; P.sd = 1; P.M_out = M_out;
   P.mode = resample_mode; P.alpha = 1.0f;
   P.logits_in = logits; P.uniforms = uniforms; P.idx_out = (long long*)idx_out;
-  return launch_normalize_resample(P, (cudaStream_t)stream);
+  return launch_normalize_resample(P, workspace, (cudaStream_t)stream);
 }
 
 static int fill_ekf(EkfParams& P, const mmf_ekf_model* models, int F) {

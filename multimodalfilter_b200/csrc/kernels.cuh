@@ -48,7 +48,8 @@ int launch_traj_rows(const mmf_pf_model* model, int N, const float* controls, co
 int launch_fuse_loglik(int N, int M, int K, const float* ll, const float* w, float* out, cudaStream_t stream);
 int launch_pf_init(int N, int M, int sd, const float* mean, const float* cov, const float* eps, float* states,
                    float* logw, cudaStream_t stream);
-int launch_normalize_resample(const ResampleParams& P, cudaStream_t stream);
+int launch_normalize_resample(const ResampleParams& P, void* workspace, cudaStream_t stream);
+size_t resample_workspace_bytes(int N, int M);
 int launch_ekf(const EkfParams& P, int sd, cudaStream_t stream);
 int launch_kf_fuse(int K, long long rows, int sd, const float* mu, const float* Pk, const float* beta,
                    float* mean_out, float* cov_out, int unimodal, cudaStream_t stream);

@@ -42,26 +42,72 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return r;
 }
 
+// The pinned search predicate is  q(c) = [(double) fl(c / total) < u]  (DESIGN.md "Resampling arithmetic").
+// fl(c / total) is monotone in c, so q(c) <=> c < c*, with c* the smallest non-negative float for which q is
+// false.  c* is found once per draw with a handful of exact evaluations of q around fl(u * total); the binary
+// search then compares raw CDF entries with c*: every probe takes the same decision as the division-based
+// definition (so indices stay bit-identical), at one FSETP per probe instead of an IEEE division.
+__device__ __forceinline__ bool q_pred(float c, float total, double u) { return (double)__fdiv_rn(c, total) < u; }
+
+__device__ __forceinline__ float cdf_threshold(float total, double u) {
+  if (!(u > 0.0)) return 0.0f;  // q is false everywhere
+  float c = (float)(u * (double)total);
+  if (!(c > 0.0f)) c = __int_as_float(1);
+  for (int it = 0; it < 64; ++it) {  // walk down while the predecessor already fails q
+    const float pm = __int_as_float(__float_as_int(c) - 1);
+    if (c > 0.0f && !q_pred(pm, total, u)) c = pm; else break;
+  }
+  for (int it = 0; it < 64 && q_pred(c, total, u); ++it) c = __int_as_float(__float_as_int(c) + 1);
+  return c;
+}
+
 __device__ __forceinline__ int lower_bound_cdf(const float* cdf, int M, float total, double u) {
+  // Fast path: search against c0 = fl(u * total), which is within ~2 ulp of c*.  A probe can only decide
+  // differently from the definition if the probed entry lies between c0 and c*, i.e. within a few ulp of c0;
+  // if any probed entry was that close, redo the search with the exact threshold.
+  const float c0 = (float)(u * (double)total);
+  const float band = fmaxf(c0 * 4.8e-7f, 1e-37f);  // >= 4 ulp of c0
   int lo = 0, hi = M;
+  bool near = false;
   while (lo < hi) {
     const int mid = lo + ((hi - lo) >> 1);
-    const float c = __fdiv_rn(cdf[mid], total);
-    if ((double)c < u) lo = mid + 1; else hi = mid;
+    const float c = cdf[mid];
+    near |= fabsf(c - c0) <= band;
+    if (c < c0) lo = mid + 1; else hi = mid;
+  }
+  if (near || !(u > 0.0)) {
+    const float cstar = cdf_threshold(total, u);
+    lo = 0;
+    hi = M;
+    while (lo < hi) {
+      const int mid = lo + ((hi - lo) >> 1);
+      if (cdf[mid] < cstar) lo = mid + 1; else hi = mid;
+    }
   }
   return lo < M - 1 ? lo : M - 1;
 }
 
-__global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_constant__ ResampleParams P) {
+// per-trajectory scratch arrays, in floats: [cdf Mpad | segoff Mpad/8 | gtot Mpad/256 + 4 | diff Mpad]
+__host__ __device__ inline size_t trajectory_scratch_floats(int M, bool soft) {
+  const size_t Mpad = ((size_t)(M + GROUP - 1) / GROUP) * GROUP;
+  const size_t n = Mpad + Mpad / SEG + Mpad / GROUP + 4 + (soft ? Mpad : 0);
+  return (n + 63) & ~(size_t)63;  // slices stay 256-byte aligned (vector loads in the serial scan)
+}
+
+// GLOBAL_WS = false: the trajectory's arrays live in shared memory (M up to ~48 k);
+// GLOBAL_WS = true : they live in a caller-provided global workspace, one slice per CTA (any M: the
+//                    1 k ... 1 M particle sweep of BASELINE config C5 runs through this instantiation).
+template <bool GLOBAL_WS>
+__global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_constant__ ResampleParams P, float* workspace) {
   extern __shared__ __align__(16) float sm[];
+  __shared__ float scratch[32];
   const int M = P.M, sd = P.sd, tid = threadIdx.x;
   const int Mpad = ((M + GROUP - 1) / GROUP) * GROUP;
-  float* scratch = sm;            // 32
-  float* cdf = sm + 32;           // Mpad   (log-weights first, CDF later)
-  float* segoff = cdf + Mpad;     // Mpad / SEG
-  float* gtot = segoff + Mpad / SEG;  // Mpad / GROUP (+1)
-  float* diff = gtot + Mpad / GROUP + 4;  // M (only when alpha < 1): logw - logits
   const bool soft = P.alpha < 1.0f;
+  float* cdf = GLOBAL_WS ? workspace + (size_t)blockIdx.x * trajectory_scratch_floats(M, soft) : sm;  // log-weights first, CDF later
+  float* segoff = cdf + Mpad;     // Mpad / SEG
+  float* gtot = segoff + Mpad / SEG;  // Mpad / GROUP (+4)
+  float* diff = gtot + Mpad / GROUP + 4;  // Mpad (only when alpha < 1): logw - logits
   const bool resample = P.mode != MMF_RESAMPLE_NONE;
 
   for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
@@ -163,11 +209,27 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
     // ---- CDF --------------------------------------------------------------------------------------------
     const bool strict = (P.mode == MMF_RESAMPLE_MULTINOMIAL_STRICT || P.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT);
     if (strict) {
+      // The chain of M dependent fp32 adds IS the definition (torch.multinomial's CPU order), so it cannot be
+      // parallelised; what can be done is keep everything but the adds off the critical path: 16 values are
+      // fetched per iteration with vector loads (independent of the running sum) and written back vectorised,
+      // leaving 4 cycles per element.  Other CTAs on the SM overlap their streaming phases with it.
       if (tid == 0) {
         float run = 0.0f;
-        for (int i = 0; i < M; ++i) {
-          run = __fadd_rn(run, cdf[i]);
-          cdf[i] = run;
+        float4* c4 = reinterpret_cast<float4*>(cdf);
+        const int blocks16 = Mpad / 16;  // padded entries are zero: adding them is exact and harmless
+        for (int b = 0; b < blocks16; ++b) {
+          float4 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = c4[b * 4 + q];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            run = __fadd_rn(run, v[q].x); v[q].x = run;
+            run = __fadd_rn(run, v[q].y); v[q].y = run;
+            run = __fadd_rn(run, v[q].z); v[q].z = run;
+            run = __fadd_rn(run, v[q].w); v[q].w = run;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) c4[b * 4 + q] = v[q];
         }
       }
       __syncthreads();
@@ -232,37 +294,63 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
   }
 }
 
-static size_t resample_smem_bytes(int M, bool soft) {
-  const int Mpad = ((M + GROUP - 1) / GROUP) * GROUP;
-  size_t floats = 32 + (size_t)Mpad + Mpad / SEG + Mpad / GROUP + 4 + (soft ? M : 0);
-  return floats * sizeof(float);
-}
+static size_t resample_smem_bytes(int M, bool soft) { return trajectory_scratch_floats(M, soft) * sizeof(float); }
 
-int launch_normalize_resample(const ResampleParams& P, cudaStream_t stream) {
-  const bool soft = P.alpha < 1.0f;
-  const size_t smem = resample_smem_bytes(P.M, soft);
+static int resample_window(size_t* window_out) {
   static thread_local int configured_dev = -1;
   static thread_local size_t window = 0;
   int dev = 0;
   MMF_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    int rc = opt_in_shared_memory(k_normalize_resample, &window);
+    int rc = opt_in_shared_memory(k_normalize_resample<false>, &window);
     if (rc) return rc;
     configured_dev = dev;
   }
-  if (smem > window) {
-    set_error("normalize_resample: M=%d needs %zu B of shared memory (window %zu B); the large-M path is not built yet",
-              P.M, smem, window);
-    return MMF_E_UNSUPPORTED;
-  }
-  int sms = 148;
+  *window_out = window;
+  return MMF_OK;
+}
+
+constexpr int WS_CTAS_PER_SM = 4;
+
+// bytes of global workspace mmf_pf_normalize_resample / mmf_resample need for (N, M): 0 when a trajectory
+// fits shared memory, else one scratch slice per resident CTA
+size_t resample_workspace_bytes(int N, int M) {
+  size_t window = 0;
+  if (resample_window(&window) != MMF_OK) window = 200 * 1024;
+  if (resample_smem_bytes(M, true) <= window) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = (long long)sms * WS_CTAS_PER_SM;
+  if (grid > N) grid = N;
+  return (size_t)grid * trajectory_scratch_floats(M, true) * sizeof(float);
+}
+
+int launch_normalize_resample(const ResampleParams& P, void* workspace, cudaStream_t stream) {
+  const bool soft = P.alpha < 1.0f;
+  const size_t smem = resample_smem_bytes(P.M, soft);
+  size_t window = 0;
+  int rc = resample_window(&window);
+  if (rc) return rc;
+  int dev = 0, sms = 148;
+  MMF_CUDA(cudaGetDevice(&dev));
   MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (smem > window) {
+    MMF_REQUIRE(workspace != nullptr,
+                "normalize_resample: M=%d does not fit shared memory; pass a workspace of mmf_pf_resample_workspace_bytes() bytes",
+                P.M);
+    long long grid = (long long)sms * WS_CTAS_PER_SM;
+    if (grid > P.N) grid = P.N;
+    k_normalize_resample<true><<<(int)grid, NR_TPB, 0, stream>>>(P, static_cast<float*>(workspace));
+    MMF_LAUNCH_CHECK("k_normalize_resample<global>");
+    return MMF_OK;
+  }
   // enough CTAs per SM to hide the serial CDF chain of one trajectory behind the others
   int per_sm = (int)((200 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
   long long grid = (long long)sms * per_sm;
   if (grid > P.N) grid = P.N;
-  k_normalize_resample<<<(int)grid, NR_TPB, smem, stream>>>(P);
+  k_normalize_resample<false><<<(int)grid, NR_TPB, smem, stream>>>(P, nullptr);
   MMF_LAUNCH_CHECK("k_normalize_resample");
   return MMF_OK;
 }

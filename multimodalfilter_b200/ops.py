@@ -145,6 +145,21 @@ def pf_predict_measure(model_struct, states, eps, rowbias, logw, modality_logw, 
     return (states_out, logw_out, ll) if want_ll else (states_out, logw_out)
 
 
+_WORKSPACES = {}
+
+
+def _resample_workspace(N, M, device):
+    """Global scratch for trajectories that do not fit shared memory (cached per device, grown on demand)."""
+    need = _lib.load().mmf_pf_resample_workspace_bytes(N, M)
+    if need == 0:
+        return None
+    buf = _WORKSPACES.get(device)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
+        _WORKSPACES[device] = buf
+    return buf
+
+
 def pf_normalize_resample(states, logw_unnorm, *, estimation=ESTIMATE_WEIGHTED_AVERAGE, mode=RESAMPLE_NONE,
                           alpha=1.0, M_out=None, uniforms=None, want_debug=False):
     """Second half of R6 + R7.  Returns dict(states, logw, estimate[, logw_norm, logits, idx])."""
@@ -169,12 +184,13 @@ def pf_normalize_resample(states, logw_unnorm, *, estimation=ESTIMATE_WEIGHTED_A
     logw_norm = torch.empty((N, M), device=dev, dtype=torch.float32) if want_debug else None
     logits = torch.empty((N, M), device=dev, dtype=torch.float32) if (want_debug and resample) else None
     idx = torch.empty((N, M_out), device=dev, dtype=torch.int64) if (want_debug and resample) else None
+    ws = _resample_workspace(N, M, dev)
     _lib.check(
         PROFILE.run(
             "pf_normalize_resample", 1, lib.mmf_pf_normalize_resample,
             N, M, sd, _lib.ptr(states), _lib.ptr(logw_unnorm), estimation, mode, float(alpha), M_out,
             _lib.ptr(uniforms), _lib.ptr(states_out), _lib.ptr(logw_out), _lib.ptr(est), _lib.ptr(logw_norm),
-            _lib.ptr(logits), _lib.ptr(idx), None, _lib.stream_of(states),
+            _lib.ptr(logits), _lib.ptr(idx), _lib.ptr(ws), _lib.stream_of(states),
         )
     )
     out = {"states": states_out if resample else states, "logw": logw_out, "estimate": est}
@@ -204,8 +220,9 @@ def resample_indices(logits, uniforms, mode=RESAMPLE_MULTINOMIAL_STRICT, M_out=N
     if M_out is None:
         M_out = M if is_systematic(mode) else uniforms.shape[1]
     idx = torch.empty((N, M_out), device=logits.device, dtype=torch.int64)
+    ws = _resample_workspace(N, M, logits.device)
     _lib.check(
-        PROFILE.run("resample", 1, lib.mmf_resample, N, M, M_out, _lib.ptr(logits), mode, _lib.ptr(uniforms), _lib.ptr(idx), None,
+        PROFILE.run("resample", 1, lib.mmf_resample, N, M, M_out, _lib.ptr(logits), mode, _lib.ptr(uniforms), _lib.ptr(idx), _lib.ptr(ws),
                          _lib.stream_of(logits))
     )
     return idx

@@ -65,7 +65,8 @@ def test_fuse_loglik(N, M, K, weighted):
 
 
 # ---- R7 standalone: bit-exact indices ------------------------------------------------------------------
-RESAMPLE_CASES = [(8, 30, 30), (4, 300, 300), (6, 1000, 1000), (3, 257, 64), (2, 1, 5), (5, 2, 9), (2, 4096, 4096), (1, 10000, 777)]
+RESAMPLE_CASES = [(8, 30, 30), (4, 300, 300), (6, 1000, 1000), (3, 257, 64), (2, 1, 5), (5, 2, 9), (2, 4096, 4096), (1, 10000, 777),
+                  (2, 70000, 5000), (1, 300000, 1000)]  # the last two exceed shared memory: global-workspace path (config C5)
 
 
 @pytest.mark.parametrize("mode", ["multinomial", "multinomial_fast", "systematic", "systematic_fast"])
@@ -135,6 +136,7 @@ def test_pinned_arithmetic_differs_from_torch_only_at_cdf_ties():
     (5, 30, 2, 300, 1.0, "weighted_average"),   # eval after train: particle count grows (quirk Q8)
     (4, 100, 3, 100, 0.5, "weighted_average"),  # soft resampling
     (2, 1, 2, 1, 1.0, "weighted_average"),
+    (2, 100000, 2, 100000, 1.0, "weighted_average"),  # global-workspace path
 ])
 def test_normalize_estimate_resample(mode, N, M, sd, M_out, alpha, estimation):
     if mode == "none" and (M_out != M or alpha != 1.0):
