@@ -87,6 +87,7 @@ typedef struct mmf_chain {
   int32_t reserved;
   const float* w;       /* packed fp32 weights, layout above */
   const void* w_mma;    /* optional tcgen05 operand pack built by mmf_pack_chain_mma (NULL => FP32 only) */
+  const void* w_bwd;    /* optional backward operand pack built by mmf_pack_chain_bwd (training only) */
 } mmf_chain;
 
 /* Per-trajectory (hoisted) part of a chain's mid layer:
@@ -210,6 +211,27 @@ int mmf_kf_fuse_unimodal(int32_t K, int32_t rows, int32_t sd, const float* mu, c
  * UMMA shared-memory layout).  dst must hold mmf_chain_mma_bytes(chain) bytes. */
 size_t mmf_chain_mma_bytes(const mmf_chain* chain);
 int mmf_pack_chain_mma(const mmf_chain* chain, void* dst, void* stream);
+
+/* ---- BPTT training support (BASELINE config C4) ------------------------------------------------
+ * Backward of the measurement heads for the case every reference curriculum trains
+ * (ref: scripts/push_task/train_push.py:154,213: dynamics frozen, no resampling in train mode, A.3/A.7):
+ * the particle states then carry no gradient to a trainable leaf, so one filter step needs
+ *   d loss / d (pre-activation) of every head layer, from which dW = delta^T a, db = sum delta,
+ *   d rowbias = sum over the trajectory's particles of delta_mid.
+ * mmf_pf_heads_forward_train: the forward step with the heads' activations saved.  states_in/eps non-NULL:
+ *   the particles are first moved through the dynamics (as in mmf_pf_predict_measure) into states_moved;
+ *   states_in == NULL: states_moved is an input (heads only).
+ *   ll_out (K, N*M) per-head log-likelihoods; act_out (K, L+1, N*M, 64): plane l = input of 64x64 layer l,
+ *   plane L = input of the output layer (L = 2 n_pre_res + 1 + 2 n_post_res); logw_scratch (N*M) is clobbered.
+ * mmf_pf_heads_backward: d_ll (K, N*M) -> delta_out (K, L+1, N*M, 64): plane l = delta of 64x64 layer l,
+ *   plane L = delta of the input layer (Linear(sd, 64) + ReLU). */
+size_t mmf_chain_bwd_bytes(const mmf_chain* chain);
+int mmf_pack_chain_bwd(const mmf_chain* chain, void* dst, void* stream);
+int mmf_pf_heads_forward_train(const mmf_pf_model* model, int32_t N, int32_t M, const float* states_in,
+                               const float* eps, float* states_moved, const float* rowbias, uint32_t enabled_mask,
+                               int32_t precision, float* ll_out, float* act_out, float* logw_scratch, void* stream);
+int mmf_pf_heads_backward(const mmf_pf_model* model, int32_t N, int32_t M, const float* act, const float* d_ll,
+                          uint32_t enabled_mask, float* delta_out, void* stream);
 
 #ifdef __cplusplus
 }

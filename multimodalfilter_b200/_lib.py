@@ -33,6 +33,7 @@ class Chain(C.Structure):
         ("reserved", C.c_int32),
         ("w", C.c_void_p),
         ("w_mma", C.c_void_p),
+        ("w_bwd", C.c_void_p),
     ]
 
 
@@ -95,6 +96,11 @@ PROTOTYPES = {
     "mmf_dynamics_jacobian": (C.c_int, [C.POINTER(EKFModel), _i32, _vp, _vp, _vp, _vp, _vp]),
     "mmf_kf_fuse_crossmodal": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmf_kf_fuse_unimodal": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_chain_bwd_bytes": (_sz, [C.POINTER(Chain)]),
+    "mmf_pack_chain_bwd": (C.c_int, [C.POINTER(Chain), _vp, _vp]),
+    "mmf_pf_heads_forward_train": (
+        C.c_int, [C.POINTER(PFModel), _i32, _i32, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp]),
+    "mmf_pf_heads_backward": (C.c_int, [C.POINTER(PFModel), _i32, _i32, _vp, _vp, _u32, _vp, _vp]),
     "mmf_chain_mma_bytes": (_sz, [C.POINTER(Chain)]),
     "mmf_pack_chain_mma": (C.c_int, [C.POINTER(Chain), _vp, _vp]),
 }

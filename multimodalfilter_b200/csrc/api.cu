@@ -237,4 +237,40 @@ int mmf_pack_chain_mma(const mmf_chain* chain, void* dst, void* stream) {
   return pack_chain_mma(chain, dst, (cudaStream_t)stream);
 }
 
+size_t mmf_chain_bwd_bytes(const mmf_chain* chain) { return chain ? chain_bwd_bytes(chain) : 0; }
+
+int mmf_pack_chain_bwd(const mmf_chain* chain, void* dst, void* stream) {
+  MMF_REQUIRE(chain && dst, "pack_chain_bwd: NULL argument");
+  return pack_chain_bwd(chain, dst, (cudaStream_t)stream);
+}
+
+int mmf_pf_heads_forward_train(const mmf_pf_model* model, int32_t N, int32_t M, const float* states_in,
+                               const float* eps, float* states_moved, const float* rowbias, uint32_t enabled_mask,
+                               int32_t precision, float* ll_out, float* act_out, float* logw_scratch, void* stream) {
+  int rc = validate_pf_model(model);
+  if (rc) return rc;
+  MMF_REQUIRE(N >= 0 && M >= 1, "heads_forward_train: bad shape N=%d M=%d", N, M);
+  if (N == 0) return MMF_OK;
+  MMF_REQUIRE(states_moved && rowbias && ll_out && act_out && logw_scratch, "heads_forward_train: NULL buffer");
+  MMF_REQUIRE(precision == MMF_PREC_BF16X3 || precision == MMF_PREC_BF16, "heads_forward_train: tensor-core precisions only");
+  const uint32_t all = (1u << model->num_heads) - 1u;
+  MMF_REQUIRE((enabled_mask & all) != 0, "heads_forward_train: no head enabled");
+  MMF_REQUIRE((states_in == nullptr) == (eps == nullptr), "heads_forward_train: states_in and eps go together");
+  return launch_particle_chain_tc(model, N, M, states_in, eps, rowbias, logw_scratch, nullptr, enabled_mask & all,
+                                  precision, states_moved, logw_scratch, ll_out, (cudaStream_t)stream,
+                                  /*first_chain=*/states_in ? 0 : 1, act_out);
+}
+
+int mmf_pf_heads_backward(const mmf_pf_model* model, int32_t N, int32_t M, const float* act, const float* d_ll,
+                          uint32_t enabled_mask, float* delta_out, void* stream) {
+  int rc = validate_pf_model(model);
+  if (rc) return rc;
+  MMF_REQUIRE(N >= 0 && M >= 1, "heads_backward: bad shape N=%d M=%d", N, M);
+  if (N == 0) return MMF_OK;
+  MMF_REQUIRE(act && d_ll && delta_out, "heads_backward: NULL buffer");
+  const uint32_t all = (1u << model->num_heads) - 1u;
+  MMF_REQUIRE((enabled_mask & all) != 0, "heads_backward: no head enabled");
+  return launch_head_chain_bwd(model, N, M, act, d_ll, enabled_mask & all, delta_out, (cudaStream_t)stream);
+}
+
 }  // extern "C"

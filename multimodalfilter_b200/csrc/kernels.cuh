@@ -42,7 +42,8 @@ int launch_particle_chain_ffma(const mmf_pf_model* model, int N, int M, const fl
                                float* states_out, float* logw_out, float* ll_out, cudaStream_t stream);
 int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
                              const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
-                             int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream);
+                             int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream,
+                             int first_chain = 0, float* act_out = nullptr);
 int launch_traj_rows(const mmf_pf_model* model, int N, const float* controls, const float* const* obs_feats,
                      float* out, cudaStream_t stream);
 int launch_fuse_loglik(int N, int M, int K, const float* ll, const float* w, float* out, cudaStream_t stream);
@@ -53,6 +54,10 @@ size_t resample_workspace_bytes(int N, int M);
 int launch_ekf(const EkfParams& P, int sd, cudaStream_t stream);
 int launch_kf_fuse(int K, long long rows, int sd, const float* mu, const float* Pk, const float* beta,
                    float* mean_out, float* cov_out, int unimodal, cudaStream_t stream);
+size_t chain_bwd_bytes(const mmf_chain* chain);
+int pack_chain_bwd(const mmf_chain* chain, void* dst, cudaStream_t stream);
+int launch_head_chain_bwd(const mmf_pf_model* model, int N, int M, const float* act, const float* d_ll, uint32_t enabled,
+                          float* delta_out, cudaStream_t stream);
 size_t chain_mma_bytes(const mmf_chain* chain);
 int pack_chain_mma(const mmf_chain* chain, void* dst, cudaStream_t stream);
 

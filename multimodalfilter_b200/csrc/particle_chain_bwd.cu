@@ -1,0 +1,303 @@
+// particle_chain_bwd.cu -- backward of the per-particle measurement heads for BPTT training
+// (BASELINE config C4: push crossmodal PF, no resampling, MSE on the estimates).
+//
+// With the dynamics frozen -- as in every training curriculum of the reference
+// (ref: scripts/push_task/train_push.py:154,213) -- the particle states carry no gradient to a trainable
+// leaf, so what BPTT needs per filter step is, for every enabled head k and particle:
+//     delta_l = d loss / d (pre-activation of layer l),  l = input layer, the 64x64 layers
+// from which the host forms dW_l = delta_l^T a_l, db_l = sum delta_l, and d rowbias = sum_m delta_mid.
+// The activations a_l come from the forward kernel (k_particle_chain_tc, act_out).
+//
+// Same machine as the forward: a group of 128 threads owns a 128-particle tile, thread = particle row = TMEM
+// lane; delta_l (bf16 hi/lo split, TMEM) x W_l (smem, K-major SW128, here with K = OUTPUT features) ->
+// gradient w.r.t. the layer input (TMEM, fp32), tcgen05.mma TS form, 3 MMAs per K step; the epilogue adds the
+// residual branch, applies the ReLU mask read from the saved activation, stores delta_l and feeds the next GEMM.
+//
+// Replaces (for the heads) what autograd does for ref: crossmodal/push_models/pf.py:91-109 in
+// torchfilter.train.train_filter (A.7; call site ref: crossmodal/train_helpers.py:155-162).
+#include "tc_common.cuh"
+
+namespace mmf {
+
+// ---- backward operand image of one chain ----------------------------------------------------------------
+//   [layer 0 hi | layer 0 lo | ... | layer L-1 hi | layer L-1 lo]   B[n = input feature][k = output feature] = W[k][n]
+//   [out_W[out_dim][64]]                                            fp32 (gradient of the output layer, CUDA cores)
+__host__ __device__ inline size_t bwd_image_tiles_bytes(const ChainDev& c) { return (size_t)chain_layers(c) * 2 * TILE_B; }
+__host__ __device__ inline size_t bwd_image_bytes(const ChainDev& c) {
+  const size_t b = bwd_image_tiles_bytes(c) + sizeof(float) * (size_t)(c.out_dim * U);
+  return (b + 1023) & ~(size_t)1023;
+}
+
+__global__ void k_pack_chain_bwd(ChainDev ch, uint8_t* __restrict__ dst) {
+  const int L = chain_layers(ch);
+  const float* w = ch.w;
+  const int off_first_res = ch.in_dim * U + U;
+  const int off_mid = off_first_res + ch.n_pre * RES_FLOATS;
+  const int off_post = off_mid + U * U;
+  const int off_out = off_post + ch.n_post * RES_FLOATS;
+  float* fdst = reinterpret_cast<float*>(dst + bwd_image_tiles_bytes(ch));
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int layer = 0; layer < L; ++layer) {
+    const float* Wt;  // packed transposed weights: Wt[k_in][j_out] = W[j_out][k_in]
+    if (layer < 2 * ch.n_pre) {
+      Wt = w + off_first_res + (layer >> 1) * RES_FLOATS + (layer & 1) * (U * U + U);
+    } else if (layer == 2 * ch.n_pre) {
+      Wt = w + off_mid;
+    } else {
+      const int rel = layer - 2 * ch.n_pre - 1;
+      Wt = w + off_post + (rel >> 1) * RES_FLOATS + (rel & 1) * (U * U + U);
+    }
+    uint8_t* hi = dst + (size_t)layer * 2 * TILE_B;
+    uint8_t* lo = hi + TILE_B;
+    for (int e = tid; e < U * U; e += nth) {
+      const int n = e / U, k = e % U;  // B[n = in][k = out] = W[k][n] = Wt[n][k]
+      const float v = Wt[n * U + k];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      const int o = sw128_offset(n, k);
+      *reinterpret_cast<__nv_bfloat16*>(hi + o) = h;
+      *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
+    }
+  }
+  for (int e = tid; e < ch.out_dim * U; e += nth) fdst[e] = w[off_out + e];
+}
+
+size_t chain_bwd_bytes(const mmf_chain* chain) { return bwd_image_bytes(to_dev(*chain)); }
+
+int pack_chain_bwd(const mmf_chain* chain, void* dst, cudaStream_t stream) {
+  MMF_REQUIRE(chain->w != nullptr, "pack_chain_bwd: chain has no fp32 weights");
+  MMF_REQUIRE(((uintptr_t)dst & 15) == 0, "pack_chain_bwd: destination must be 16-byte aligned");
+  k_pack_chain_bwd<<<16, 256, 0, stream>>>(to_dev(*chain), static_cast<uint8_t*>(dst));
+  MMF_LAUNCH_CHECK("k_pack_chain_bwd");
+  return MMF_OK;
+}
+
+struct BwdParams {
+  ChainDev chains[MMF_MAX_HEADS];
+  const uint8_t* images[MMF_MAX_HEADS];
+  int K;
+  uint32_t enabled;
+  long long total;
+  size_t image_cap;
+  const float* act;     // (K, L+1, P, 64): activation feeding GEMM layer l (index l), the output layer (index L)
+  const float* d_ll;    // (K, P): d loss / d log-likelihood of head k
+  float* delta_out;     // (K, L+1, P, 64): delta of GEMM layer l (index l), of the input layer (index L)
+};
+
+enum { LK_RES_A = 0, LK_RES_B = 1, LK_MID = 2 };
+__device__ __forceinline__ int layer_kind(const ChainDev& ch, int layer) {
+  const int mid_at = 2 * ch.n_pre;
+  if (layer == mid_at) return LK_MID;
+  const int rel = layer < mid_at ? layer : layer - mid_at - 1;
+  return (rel & 1) ? LK_RES_B : LK_RES_A;
+}
+
+// One 16-column slice of "next delta = (grad [+ skip]) * relu'(activation)": stores it, keeps the skip branch,
+// and (feed != 0) writes it as the next A operand.
+__device__ __forceinline__ void delta_chunk(float2 (&v)[8], const float* __restrict__ act_row, float* __restrict__ delta_row,
+                                            float2 (&gres)[U / 2], int chunk, bool add_res, bool mask, bool set_res,
+                                            bool feed, uint32_t tAhi, uint32_t tAlo) {
+  const float4* a4 = reinterpret_cast<const float4*>(act_row + chunk * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = mask ? __ldg(a4 + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+    float2 g0 = v[2 * q], g1 = v[2 * q + 1];
+    if (add_res) {
+      g0 = __fadd2_rn(g0, gres[chunk * 8 + 2 * q]);
+      g1 = __fadd2_rn(g1, gres[chunk * 8 + 2 * q + 1]);
+    }
+    g0.x = a.x > 0.0f ? g0.x : 0.0f;
+    g0.y = a.y > 0.0f ? g0.y : 0.0f;
+    g1.x = a.z > 0.0f ? g1.x : 0.0f;
+    g1.y = a.w > 0.0f ? g1.y : 0.0f;
+    v[2 * q] = g0;
+    v[2 * q + 1] = g1;
+    if (set_res) {
+      gres[chunk * 8 + 2 * q] = g0;
+      gres[chunk * 8 + 2 * q + 1] = g1;
+    }
+  }
+  if (delta_row != nullptr) {
+    float4* d4 = reinterpret_cast<float4*>(delta_row + chunk * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+  }
+  if (feed) store_a_chunk<false>(v, tAhi, tAlo, chunk, false);
+}
+
+template <int TC_GROUPS>
+__global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_head_chain_bwd(const __grid_constant__ BwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + P.image_cap);
+  uint64_t* gbar = wbar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbar + TC_MAX_GROUPS);
+
+  const int tid = threadIdx.x, row = tid & 127;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int g = warp >> 2;
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int i = 0; i < TC_GROUPS; ++i) mbar_init(gbar + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t grp_cols = tmem_base + g * 128;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t tD = grp_cols + lane_off;
+  const uint32_t tAhi = tD + 64, tAlo = tD + 96;
+  uint32_t wphase = 0, gphase = 0;
+  const long long tiles = (P.total + 127) / 128;
+  constexpr uint32_t IDESC = make_idesc(64, 128);
+  const size_t plane = (size_t)P.total * U;
+
+  for (int k = 0; k < P.K; ++k) {
+    if (!((P.enabled >> k) & 1u)) continue;
+    const ChainDev ch = P.chains[k];
+    const int L = chain_layers(ch);
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)bwd_image_bytes(ch);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(wbar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768) {
+        const uint32_t n = bytes - off < 32768 ? bytes - off : 32768;
+        bulk_g2s(smem + off, P.images[k] + off, n, wbar);
+      }
+    }
+    mbar_wait(wbar, wphase);
+    wphase ^= 1;
+    const uint32_t tiles_addr = smem_u32(smem);
+    const float* out_W = reinterpret_cast<const float*>(smem + bwd_image_tiles_bytes(ch));  // row 0: the head's scalar output
+
+    for (long long tile = (long long)blockIdx.x * TC_GROUPS + g; tile < tiles; tile += (long long)gridDim.x * TC_GROUPS) {
+      const long long p_raw = tile * 128 + row;
+      const bool live = p_raw < P.total;
+      const long long p = live ? p_raw : P.total - 1;
+      const float* act_base = P.act + ((size_t)k * (L + 1) * P.total + (size_t)p) * U;
+      float* delta_base = P.delta_out + ((size_t)k * (L + 1) * P.total + (size_t)p) * U;
+      const float dll = live ? P.d_ll[(size_t)k * P.total + p] : 0.0f;
+
+      // ---- output layer: grad w.r.t. its input = dll * out_W[0]; delta of layer L-1 -------------------------
+      float2 gres[U / 2];
+#pragma unroll
+      for (int j = 0; j < U / 2; ++j) gres[j] = make_float2(0.0f, 0.0f);
+      {
+        const int kind = layer_kind(ch, L - 1);
+        const bool mask = (kind != LK_MID) || ch.mid_relu;
+        const float4* w4 = reinterpret_cast<const float4*>(out_W);
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          float2 v[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 w = w4[chunk * 4 + q];
+            v[2 * q] = make_float2(w.x * dll, w.y * dll);
+            v[2 * q + 1] = make_float2(w.z * dll, w.w * dll);
+          }
+          delta_chunk(v, act_base + (size_t)L * plane, live ? delta_base + (size_t)(L - 1) * plane : nullptr, gres, chunk,
+                      false, mask, kind == LK_RES_B, true, tAhi, tAlo);
+        }
+      }
+
+      // ---- 64x64 layers, last to first -----------------------------------------------------------------------------
+      for (int layer = L - 1; layer >= 0; --layer) {
+        tc_wait_st();
+        tc_fence_before();
+        group_bar(1 + g, 128);
+        if ((warp & 3) == 0 && elect_one_sync()) {
+          tc_fence_after();
+          const uint32_t hi_addr = tiles_addr + (uint32_t)layer * 2 * TILE_B;
+          const uint64_t bhi = make_b_desc(hi_addr), blo = make_b_desc(hi_addr + TILE_B);
+          const uint32_t a_hi = grp_cols + 64, a_lo = grp_cols + 96;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) mma_ts(grp_cols, a_hi + kk * 8, bhi + (uint64_t)(kk * 2), IDESC, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) mma_ts(grp_cols, a_hi + kk * 8, blo + (uint64_t)(kk * 2), IDESC, 1);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) mma_ts(grp_cols, a_lo + kk * 8, bhi + (uint64_t)(kk * 2), IDESC, 1);
+          tc_commit(gbar + g);
+        }
+        mbar_wait(gbar + g, gphase);
+        gphase ^= 1;
+        tc_fence_after();
+
+        // D = gradient w.r.t. the input of `layer`; turn it into the delta of the producer of that input
+        const int kind = layer_kind(ch, layer);
+        const bool add_res = (kind == LK_RES_A);  // the block input also feeds the skip connection
+        const int prod = layer - 1;               // producer: GEMM layer `prod`, or the input layer when < 0
+        const int pkind = prod >= 0 ? layer_kind(ch, prod) : LK_RES_A;
+        const bool mask = prod < 0 || pkind != LK_MID || ch.mid_relu;
+        const bool set_res = prod >= 0 && pkind == LK_RES_B;
+        float* drow = live ? delta_base + (size_t)(prod >= 0 ? prod : L) * plane : nullptr;
+        const float* arow = act_base + (size_t)layer * plane;
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          uint32_t d[16];
+          tmem_ld16(tD + chunk * 16, d);
+          tc_wait_ld();
+          float2 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = make_float2(__uint_as_float(d[2 * j]), __uint_as_float(d[2 * j + 1]));
+          delta_chunk(v, arow, drow, gres, chunk, add_res, mask, set_res, prod >= 0, tAhi, tAlo);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+int launch_head_chain_bwd(const mmf_pf_model* model, int N, int M, const float* act, const float* d_ll, uint32_t enabled,
+                          float* delta_out, cudaStream_t stream) {
+  BwdParams P;
+  P.K = model->num_heads;
+  size_t cap = 0;
+  int L0 = -1;
+  for (int k = 0; k < P.K; ++k) {
+    P.chains[k] = to_dev(model->heads[k]);
+    P.images[k] = static_cast<const uint8_t*>(model->heads[k].w_bwd);
+    if ((enabled >> k) & 1u) {
+      MMF_REQUIRE(P.images[k] != nullptr, "head %d has no backward operand image: call mmf_pack_chain_bwd first", k);
+      const size_t b = bwd_image_bytes(P.chains[k]);
+      cap = b > cap ? b : cap;
+    }
+    const int L = chain_layers(P.chains[k]);
+    MMF_REQUIRE(L0 < 0 || L == L0, "heads_backward: all heads must have the same depth");
+    L0 = L;
+  }
+  P.image_cap = cap;
+  P.enabled = enabled;
+  P.total = (long long)N * M;
+  P.act = act;
+  P.d_ll = d_ll;
+  P.delta_out = delta_out;
+  const size_t smem = cap + 1024;
+  static thread_local int configured_dev = -1;
+  static thread_local size_t window = 0;
+  int dev = 0, sms = 148;
+  MMF_CUDA(cudaGetDevice(&dev));
+  MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (configured_dev != dev) {
+    int rc = opt_in_shared_memory(k_head_chain_bwd<4>, &window);
+    if (rc) return rc;
+    configured_dev = dev;
+  }
+  MMF_REQUIRE(smem <= window, "heads_backward needs %zu B of shared memory (window %zu B)", smem, window);
+  const long long tiles = (P.total + 127) / 128;
+  long long grid = (tiles + 3) / 4;
+  if (grid > sms) grid = sms;
+  k_head_chain_bwd<4><<<(int)grid, 4 * 128, smem, stream>>>(P);
+  MMF_LAUNCH_CHECK("k_head_chain_bwd");
+  return MMF_OK;
+}
+
+}  // namespace mmf

@@ -22,51 +22,37 @@
 //     three orders of magnitude below the tensor time).
 //
 // Replaces the same reference lines as particle_chain_ffma.cu.
-#include <cuda_bf16.h>
-#include <stdlib.h>
-
-#include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace mmf {
 
-// GROUPS independent tile pipelines per CTA; TPR threads share one particle row (each owns 64/TPR
-// activation columns), so a group is 128*TPR threads = 4*TPR warps, all four TMEM lane quadrants
-// covered TPR times.  TMEM: 128 columns per group (64 accumulator + 32 A_hi + 32 A_lo) => GROUPS <= 4.
-constexpr int TC_MAX_GROUPS = 4;
-constexpr int TILE_B = 64 * 128;      // one 64(N) x 64(K) bf16 operand tile: 64 rows of 128 bytes
-constexpr int OUT_TILE_B = 16 * 128;  // the output layer, N padded to 16
-constexpr int OUT_PAD = 16;
+// Debug-only phase timestamps of (CTA 0, group 0, thread 0): enabled with MMF_TC_TIMESTAMPS=1, read back with
+// mmf_debug_tc_timestamps().  Layout: per layer iteration 5 clock64 stamps.
+__device__ unsigned long long g_tc_stamps[8192];
+__device__ unsigned int g_tc_stamp_count;
 
-// ---- image of one chain as it sits in shared memory (built once by k_pack_chain_mma) --------------
-//   [layer 0 hi | layer 0 lo | ... | layer L-1 hi | layer L-1 lo | out hi | out lo]   bf16, SW128 K-major
-//   [in_Wt[in_dim][64] | in_b[64] | bias[L][64] (zeros for the mid layer) | out_b[16]]  fp32
-// nsplit = 1: one CTA holds all 64 weight rows of a tile (cta_group::1).
-// nsplit = 2: CTA-pair build (cta_group::2): CTA `rank` holds rows [32 rank, 32 rank + 32) of every tile and
-//             rows [16 rank, 16 rank + 16) of the output layer, which is padded to N = 32.
-// The buffer behind mmf_chain.w_mma is [nsplit=1 image | nsplit=2 rank 0 image | nsplit=2 rank 1 image].
-__host__ __device__ inline int chain_layers(const ChainDev& c) { return 2 * c.n_pre + 1 + 2 * c.n_post; }
-__host__ __device__ inline size_t image_tiles_bytes(const ChainDev& c, int nsplit = 1) {
-  return (size_t)chain_layers(c) * 2 * (TILE_B / nsplit) + 2 * OUT_TILE_B;
-}
-__host__ __device__ inline size_t image_bytes(const ChainDev& c, int nsplit = 1) {
-  const size_t b = image_tiles_bytes(c, nsplit) + sizeof(float) * (size_t)(c.in_dim * U + U + chain_layers(c) * U + OUT_PAD);
-  return (b + 1023) & ~(size_t)1023;  // keep the concatenated images 1024-byte aligned
-}
-__host__ __device__ inline size_t image_offset(const ChainDev& c, int nsplit, int rank) {
-  return nsplit == 1 ? 0 : image_bytes(c, 1) + (size_t)rank * image_bytes(c, 2);
-}
-__host__ __device__ inline size_t image_total_bytes(const ChainDev& c) { return image_bytes(c, 1) + 2 * image_bytes(c, 2); }
-
-// byte offset of element (n, k) inside a K-major SWIZZLE_128B tile whose rows are 64 bf16 = 128 B
-__host__ __device__ inline int sw128_offset(int n, int k) {
-  return (n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2;
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
-  return r;
-}
+struct TcParams {
+  ChainDev chains[1 + MMF_MAX_HEADS];
+  const uint8_t* images[1 + MMF_MAX_HEADS];
+  int K;
+  uint32_t enabled;
+  int sd, N, M, single_pass;
+  uint32_t wait_hint_ns;
+  int stamps, use_lock;
+  int first_chain;   // 0: dynamics + heads; 1: heads only (states_out already holds the moved particles)
+  float* act_out;    // training: (K, L+1, N*M, 64) fp32 activations feeding every GEMM layer of every head, or null
+  long long total;
+  size_t image_cap;  // bytes reserved for the resident image (1024-aligned)
+  const float* states_in;
+  const float* eps;
+  const float* rowbias;
+  const float* logw_in;
+  const float* modw;
+  float* states_out;
+  float* logw_out;
+  float* ll_out;
+  float q[MMF_MAX_SD * MMF_MAX_SD];
+};
 
 __global__ void k_pack_chain_mma(ChainDev ch, uint8_t* __restrict__ base) {
   // blockIdx.y selects the image: 0 -> nsplit 1; 1, 2 -> nsplit 2 rank 0, 1
@@ -142,201 +128,6 @@ int pack_chain_mma(const mmf_chain* chain, void* dst, cudaStream_t stream) {
   return MMF_OK;
 }
 
-// ---- PTX wrappers ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)  // suspend-time hint (ns): park instead of spinning
-      : "memory");
-  return ok != 0;
-}
-// try_wait suspends in hardware for a bounded time; the spin bound turns a lost arrival into a trap
-// (a CUDA error the host sees) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 0) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity, hint_ns)) {
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// true in exactly one (converged) lane of the warp; lets ptxas keep the MMA operands in uniform registers
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void group_bar(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// D[tmem] (+)= A[tmem] * B[smem desc]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
-// CTA-pair form: one instruction covers 256 rows (128 per CTA); issued by the leader CTA only.
-__device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit2(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `target_rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target_rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(target_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0, ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (!ok && ++spins > (1u << 24)) __trap();
-  }
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
-// start address >> 4 | LBO (16 B) << 16 | SBO (8 rows x 128 B = 1024 B) << 32 | version << 46 | layout 2 << 61
-__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n, int m = 128) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-// Debug-only phase timestamps of (CTA 0, group 0, thread 0): enabled with MMF_TC_TIMESTAMPS=1, read back with
-// mmf_debug_tc_timestamps().  Layout: per layer iteration 5 clock64 stamps.
-__device__ unsigned long long g_tc_stamps[8192];
-__device__ unsigned int g_tc_stamp_count;
-
-struct TcParams {
-  ChainDev chains[1 + MMF_MAX_HEADS];
-  const uint8_t* images[1 + MMF_MAX_HEADS];
-  int K;
-  uint32_t enabled;
-  int sd, N, M, single_pass;
-  uint32_t wait_hint_ns;
-  int stamps, use_lock;
-  long long total;
-  size_t image_cap;  // bytes reserved for the resident image (1024-aligned)
-  const float* states_in;
-  const float* eps;
-  const float* rowbias;
-  const float* logw_in;
-  const float* modw;
-  float* states_out;
-  float* logw_out;
-  float* ll_out;
-  float q[MMF_MAX_SD * MMF_MAX_SD];
-};
-
-// bf16 split of 8 fp32 pairs, stored as the next A operand (columns [8*chunk, 8*chunk+8) of the hi and lo
-// regions):  hi = rz_bf16(v) (truncation == the top 16 bits of v), lo = rn_bf16(v - hi).  With RELU the
-// activation is folded into the two conversions: v < 0 gives hi = 0, and v - trunc(v) <= 0 gives lo = 0,
-// so no separate max() is needed.  5 instructions per pair: F2FP, 2 x LOP, FFMA2, F2FP.
-template <bool RELU>
-__device__ __forceinline__ void store_a_chunk(const float2 (&v)[8], uint32_t tAhi, uint32_t tAlo, int chunk,
-                                              bool single_pass) {
-  uint32_t hi[8], lo[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float2 t = make_float2(__uint_as_float(__float_as_uint(v[j].x) & 0xffff0000u),
-                                 __uint_as_float(__float_as_uint(v[j].y) & 0xffff0000u));
-    const float2 r = __ffma2_rn(t, make_float2(-1.0f, -1.0f), v[j]);
-    if (RELU) {
-      asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[j].y), "f"(v[j].x));
-      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(r.y), "f"(r.x));
-    } else {
-      asm("cvt.rz.bf16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[j].y), "f"(v[j].x));
-      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(r.y), "f"(r.x));
-    }
-  }
-  tmem_st8(tAhi + chunk * 8, hi);
-  if (!single_pass) tmem_st8(tAlo + chunk * 8, lo);
-}
-
 enum { EPI_RES_A = 0, EPI_RES_B = 1, EPI_MID_RELU = 2, EPI_MID_LINEAR = 3 };
 
 // Epilogue of one 64-wide layer for this thread's row: accumulator (TMEM) -> +bias (+residual) ->
@@ -345,9 +136,16 @@ enum { EPI_RES_A = 0, EPI_RES_B = 1, EPI_MID_RELU = 2, EPI_MID_LINEAR = 3 };
 //   RES_B : y = relu(D + b2 + xr)     xr = y
 //   MID_* : v = [relu](D + rowbias)   xr = v      (bias4 then points at the per-trajectory row in global memory)
 // tD / tAhi / tAlo / bias4 already point at this thread's first column.
+// store 16 activations of this thread's row (training: kept for the backward pass)
+__device__ __forceinline__ void store_act_chunk(float* act_row, int chunk, const float2 (&v)[8]) {
+  float4* dst = reinterpret_cast<float4*>(act_row + chunk * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+}
+
 template <int KIND, int COLS>
 __device__ __forceinline__ void epilogue(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float4* __restrict__ bias4,
-                                         float2 (&xr)[COLS / 2], bool single_pass) {
+                                         float2 (&xr)[COLS / 2], bool single_pass, float* act_row) {
   constexpr int CHUNKS = COLS / 16;
   // software pipeline over the accumulator chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c
   // is processed (tcgen05.wait::ld waits for ALL outstanding loads, so it is issued after the compute block)
@@ -375,6 +173,13 @@ __device__ __forceinline__ void epilogue(uint32_t tD, uint32_t tAhi, uint32_t tA
       }
       if (KIND != EPI_RES_A) xr[chunk * 8 + j] = a;
       v[j] = a;
+    }
+    if (act_row != nullptr) {
+      if (KIND == EPI_RES_A) {  // the stored activation needs the real max() (it is folded into the cvt below)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = make_float2(fmaxf(v[j].x, 0.0f), fmaxf(v[j].y, 0.0f));
+      }
+      store_act_chunk(act_row, chunk, v);
     }
     if (KIND == EPI_RES_A) store_a_chunk<true>(v, tAhi, tAlo, chunk, single_pass);  // relu folded into the cvt
     else store_a_chunk<false>(v, tAhi, tAlo, chunk, single_pass);
@@ -449,7 +254,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
   const long long unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
   const long long units = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
-  for (int c = 0; c <= P.K; ++c) {
+  for (int c = P.first_chain; c <= P.K; ++c) {
     if (c > 0 && !((P.enabled >> (c - 1)) & 1u)) continue;
     const ChainDev ch = P.chains[c];
     const int L = chain_layers(ch);
@@ -498,6 +303,12 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
 #pragma unroll
       for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
 
+      // training: base of this particle's saved activations for head c (layer index selects the plane)
+      float* act_base = (P.act_out != nullptr && c > 0 && live)
+                            ? P.act_out + ((size_t)(c - 1) * (L + 1) * P.total + (size_t)p) * U
+                            : nullptr;
+      const size_t act_plane = (size_t)P.total * U;
+
       // ---- input layer on the CUDA cores: xr = relu(in_W x + in_b) -> A operand ------------------------
       float2 xr[TC_COLS / 2];
       {
@@ -530,6 +341,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
             v[j].y = fmaxf(v[j].y, 0.0f);
             xr[chunk * 8 + j] = v[j];
           }
+          if (act_base != nullptr) store_act_chunk(act_base, chunk, v);
           store_a_chunk<false>(v, tAhi, tAlo, chunk, single_pass);
         }
       }
@@ -607,13 +419,15 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
         // ---- epilogue of this layer = producer of the next layer's A operand ---------------------------
         if (layer == mid_at) {
           const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
-          if (ch.mid_relu) epilogue<EPI_MID_RELU, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass);
-          else epilogue<EPI_MID_LINEAR, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass);
+          float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane : nullptr;
+          if (ch.mid_relu) epilogue<EPI_MID_RELU, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass, arow);
+          else epilogue<EPI_MID_LINEAR, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass, arow);
         } else {
           const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
           const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U);
-          if ((rel & 1) == 0) epilogue<EPI_RES_A, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass);
-          else epilogue<EPI_RES_B, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass);
+          float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane : nullptr;
+          if ((rel & 1) == 0) epilogue<EPI_RES_A, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass, arow);
+          else epilogue<EPI_RES_B, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass, arow);
         }
       }
 
@@ -673,7 +487,8 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
 
 int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
                              const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
-                             int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream) {
+                             int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream,
+                             int first_chain, float* act_out) {
   // pipeline shape: MMF_TC_VARIANT = <groups><cta group>: 41 = 4 groups, cta_group::1; 42 = 4 groups, CTA pairs
   int variant = 41;
   if (const char* env = getenv("MMF_TC_VARIANT")) variant = atoi(env);
@@ -685,7 +500,7 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
     const mmf_chain& src = (c == 0) ? model->dynamics : model->heads[c - 1];
     P.chains[c] = to_dev(src);
     P.images[c] = static_cast<const uint8_t*>(src.w_mma);
-    if (c == 0 || ((enabled >> (c - 1)) & 1u)) {
+    if ((c == 0 && first_chain == 0) || (c > 0 && ((enabled >> (c - 1)) & 1u))) {
       MMF_REQUIRE(src.w_mma != nullptr, "tensor-core chain %d has no operand image: call mmf_pack_chain_mma first", c);
       MMF_REQUIRE(((uintptr_t)src.w_mma & 15) == 0, "operand image %d must be 16-byte aligned", c);
       const size_t b = image_bytes(P.chains[c], pair ? 2 : 1);
@@ -709,6 +524,8 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
   P.ll_out = ll_out;
   for (int i = 0; i < MMF_MAX_SD * MMF_MAX_SD; ++i) P.q[i] = model->q_tril[i];
   P.wait_hint_ns = 0;
+  P.first_chain = first_chain;
+  P.act_out = act_out;
   P.stamps = getenv("MMF_TC_TIMESTAMPS") != nullptr;
   P.use_lock = 0;
   if (const char* env = getenv("MMF_TC_LOCK")) P.use_lock = atoi(env);

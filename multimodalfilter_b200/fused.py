@@ -225,6 +225,7 @@ class PFPlan:
         self.sd, self.cd = dyn_spec.sd, dyn_spec.cd
         self._sig = None
         self._buffers = None
+        self._has_bwd = False
         self.struct = None
 
     @staticmethod
@@ -252,10 +253,10 @@ class PFPlan:
             ps += list(h.head.state_layers.parameters()) + list(h.head.shared_layers.parameters())
         return ps
 
-    def refresh(self, device):
+    def refresh(self, device, backward: bool = False):
         params = self._params()
         sig = (str(device), _versions(params))
-        if sig == self._sig:
+        if sig == self._sig and (not backward or self._has_bwd):
             return
         if any(p.device != device for p in params):
             raise _lib.MMFError("filter parameters must live on the CUDA device of the inputs (call .to(device))")
@@ -276,6 +277,9 @@ class PFPlan:
         bufs.append(ops.pack_chain_mma(m.dynamics, device))
         for k in range(self.K):
             bufs.append(ops.pack_chain_mma(m.heads[k], device))
+            if backward:
+                bufs.append(ops.pack_chain_bwd(m.heads[k], device))
+        self._has_bwd = backward
         self._buffers, self.struct, self._sig = bufs, m, sig
 
     # -- per-trajectory inputs ------------------------------------------------------------------------

@@ -88,6 +88,54 @@ def pack_chain_mma(chain_struct, device):
     return buf
 
 
+def pack_chain_bwd(chain_struct, device):
+    """Backward operand image of a chain (training); stores the pointer in ``chain_struct.w_bwd``."""
+    lib = _lib.load()
+    nbytes = lib.mmf_chain_bwd_bytes(C.byref(chain_struct))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    _lib.check(lib.mmf_pack_chain_bwd(C.byref(chain_struct), _lib.ptr(buf), _lib.stream_of(buf)))
+    chain_struct.w_bwd = buf.data_ptr()
+    return buf
+
+
+def head_depth(model_struct):
+    h = model_struct.heads[0]
+    return 2 * h.n_pre_res + 1 + 2 * h.n_post_res
+
+
+def pf_heads_forward_train(model_struct, states, eps, rowbias, enabled_mask, precision=PREC_BF16X3):
+    """Training forward of one step: move the particles (dynamics, frozen) and evaluate the heads, saving the
+    activations the backward needs.  states (N,M,sd), eps (N*M,sd), rowbias (1+K,N,64) ->
+    moved (N,M,sd), ll (K,N,M), act (K,L+1,N*M,64)."""
+    lib = _lib.load()
+    N, M, sd = states.shape
+    K, L = model_struct.num_heads, head_depth(model_struct)
+    states, eps, rowbias = _f32c(states), _f32c(eps), _f32c(rowbias)
+    dev = states.device
+    moved = torch.empty_like(states)
+    ll = torch.full((K, N, M), float("nan"), device=dev, dtype=torch.float32)
+    act = torch.empty((K, L + 1, N * M, _lib.UNITS), device=dev, dtype=torch.float32)
+    scratch = torch.empty((N, M), device=dev, dtype=torch.float32)
+    _lib.check(
+        PROFILE.run("pf_heads_forward_train", 1, lib.mmf_pf_heads_forward_train, C.byref(model_struct), N, M,
+                    _lib.ptr(states), _lib.ptr(eps), _lib.ptr(moved), _lib.ptr(rowbias), enabled_mask, precision,
+                    _lib.ptr(ll), _lib.ptr(act), _lib.ptr(scratch), _lib.stream_of(states))
+    )
+    return moved, ll, act
+
+
+def pf_heads_backward(model_struct, N, M, act, d_ll, enabled_mask):
+    """d_ll (K,N,M) -> delta (K,L+1,N*M,64): plane l = delta of 64x64 layer l, plane L = delta of the input layer."""
+    lib = _lib.load()
+    act, d_ll = _f32c(act), _f32c(d_ll)
+    delta = torch.zeros_like(act)
+    _lib.check(
+        PROFILE.run("pf_heads_backward", 1, lib.mmf_pf_heads_backward, C.byref(model_struct), N, M, _lib.ptr(act),
+                    _lib.ptr(d_ll), enabled_mask, _lib.ptr(delta), _lib.stream_of(act))
+    )
+    return delta
+
+
 def pf_init(mean, covariance, eps_MNsd):
     """R2: (N,sd), (N,sd,sd), (M,N,sd) -> particle_states (N,M,sd), particle_log_weights (N,M)."""
     lib = _lib.load()

@@ -20,7 +20,7 @@ import math
 
 import torch
 
-from .. import _lib, fused, ops
+from .. import _lib, fused, ops, training
 from ..fannypack.utils import SliceWrapper
 from .base import (
     DynamicsModel,
@@ -149,7 +149,44 @@ class ParticleFilter(Filter):
         grad = _needs_grad(self, self.particle_states, self.particle_log_weights)
         if plan is not None and not grad and isinstance(controls, torch.Tensor):
             return self._step_fused(plan, observations, controls, mode, _hoisted)
+        if grad and isinstance(controls, torch.Tensor) and training.fused_train_applicable(self, plan, resample):
+            return self._step_fused_train(plan, observations, controls)
         return self._step_generic(observations, controls, resample, mode, grad)
+
+    def _step_fused_train(self, plan, observations, controls):
+        """BPTT step (train mode: no resampling; dynamics frozen): kernels for the per-particle work, torch
+        ops with autograd for the (N, M)-sized fusion / normalisation / estimate and the per-trajectory modules."""
+        states, logw = self.particle_states, self.particle_log_weights
+        N, M, sd = states.shape
+        enabled = plan.enabled()
+        plan.refresh(states.device, backward=True)
+        with torch.no_grad():
+            dyn_row = ops.pf_traj_rows(plan.struct, plan.K, controls, [None] * plan.K)[0]
+        rows, params = [], []
+        for spec, on in zip(plan.heads, enabled):
+            params += training.head_parameters(spec)
+            if not on:
+                rows.append(states.new_zeros((N, fused.U)))
+                continue
+            mid = spec.shared[0]
+            feats = spec.observation_features(observations)
+            rows.append(torch.nn.functional.linear(feats, mid.weight[:, : spec.feat_dim], mid.bias))
+        eps = self._process_eps(N * M, sd, states)
+        moved, ll = training.FusedHeads.apply(plan, states, eps, dyn_row, torch.stack(rows), plan.enabled_mask(),
+                                             ops.PRECISIONS[self.precision], *params)
+        ll = ll[[k for k, on in enumerate(enabled) if on]].permute(1, 2, 0)  # (N, M, K_enabled)
+        modw = plan.modality_log_weights(observations)
+        if modw is not None:
+            ll = ll + modw[:, enabled][:, None, :]
+        logw_unnorm = logw + torch.logsumexp(ll, dim=2)
+        logw_n = logw_unnorm - torch.logsumexp(logw_unnorm, dim=1, keepdim=True)
+        if self.estimation_method == "weighted_average":
+            estimate = torch.sum(torch.exp(logw_n)[:, :, None] * moved, dim=1)
+        else:
+            best = torch.argmax(logw_n, dim=1)
+            estimate = moved[torch.arange(N, device=best.device), best]
+        self.particle_states, self.particle_log_weights = moved, logw_n
+        return estimate
 
     def _step_fused(self, plan, observations, controls, mode, hoisted):
         states, logw = self.particle_states, self.particle_log_weights

@@ -1,0 +1,108 @@
+"""BPTT support: the fused training step of the particle filter (BASELINE config C4).
+
+In train mode torchfilter does not resample (A.3) and every curriculum of the reference freezes the
+dynamics before end-to-end training (ref: scripts/push_task/train_push.py:154,213), so the particle
+states carry no gradient to a trainable leaf; the loss reaches the parameters only through the
+log-weights.  One training step is therefore
+
+    moved, ll_k = kernel(states, eps, rows)            forward:  mmf_pf_heads_forward_train
+    d ll_k -> delta of every head layer                backward: mmf_pf_heads_backward
+    dW = delta^T a, db = sum delta, d rows_k = sum_m delta_mid      (reductions over the N*M rows)
+
+wrapped in one ``torch.autograd.Function``; the fusion log-sum-exp, the normalisation and the
+estimate are (N, M)-sized torch ops that autograd differentiates itself, and the per-trajectory
+pieces (observation encoders, the observation half of the first shared Linear, the modality weight
+model) stay ordinary torch modules, so their gradients come from autograd as well.
+"""
+from typing import List
+
+import torch
+
+from . import _lib, ops
+
+U = _lib.UNITS
+
+
+def head_parameters(spec) -> List[torch.Tensor]:
+    """Trainable tensors of one head's per-particle chain, in a fixed order (see ``_grads_for_head``)."""
+    (in_lin, pre), (mid, post, out) = spec.state, spec.shared
+    ps = [in_lin.weight, in_lin.bias]
+    for r in pre:
+        ps += [r.block1.weight, r.block1.bias, r.block2.weight, r.block2.bias]
+    ps += [mid.weight]
+    for r in post:
+        ps += [r.block1.weight, r.block1.bias, r.block2.weight, r.block2.bias]
+    ps += [out.weight, out.bias]
+    return ps
+
+
+def _grads_for_head(spec, act, delta, d_ll, moved_flat):
+    """act/delta: (L+1, P, 64); d_ll: (P,); moved_flat: (P, sd).  Returns grads in head_parameters order."""
+    (in_lin, pre), (mid, post, out) = spec.state, spec.shared
+    L = 2 * len(pre) + 1 + 2 * len(post)
+    grads = []
+    d_in = delta[L]
+    grads += [d_in.t() @ moved_flat, d_in.sum(0)]
+    layer = 0
+    for _ in pre:
+        for _half in range(2):
+            grads += [delta[layer].t() @ act[layer], delta[layer].sum(0)]
+            layer += 1
+    g_mid = torch.zeros_like(mid.weight)
+    g_mid[:, spec.feat_dim:] = delta[layer].t() @ act[layer]  # state half; the observation half flows through the rows
+    grads += [g_mid]
+    mid_layer = layer
+    layer += 1
+    for _ in post:
+        for _half in range(2):
+            grads += [delta[layer].t() @ act[layer], delta[layer].sum(0)]
+            layer += 1
+    grads += [(d_ll[None, :] @ act[L]), d_ll.sum().reshape(1)]
+    return grads, mid_layer
+
+
+class FusedHeads(torch.autograd.Function):
+    """(states, eps, dynamics row, head rows, head parameters...) -> (moved, ll[K_enabled, N, M])."""
+
+    @staticmethod
+    def forward(ctx, plan, states, eps, dyn_row, head_rows, enabled_mask, precision, *params):
+        N, M, sd = states.shape
+        dev = states.device
+        plan.refresh(dev, backward=True)
+        rowbias = torch.cat([dyn_row[None], head_rows.detach()]).contiguous()
+        moved, ll, act = ops.pf_heads_forward_train(plan.struct, states.detach(), eps, rowbias, enabled_mask,
+                                                    precision=precision)
+        ctx.plan, ctx.mask, ctx.shape = plan, enabled_mask, (N, M, sd)
+        ctx.save_for_backward(act, moved)
+        ctx.mark_non_differentiable(moved)
+        return moved, ll
+
+    @staticmethod
+    def backward(ctx, _d_moved, d_ll):
+        plan, mask = ctx.plan, ctx.mask
+        N, M, sd = ctx.shape
+        act, moved = ctx.saved_tensors
+        d_ll = torch.nan_to_num(d_ll.contiguous(), nan=0.0)
+        delta = ops.pf_heads_backward(plan.struct, N, M, act, d_ll, mask)
+        moved_flat = moved.reshape(N * M, sd)
+        d_rows = torch.zeros((plan.K, N, U), device=act.device, dtype=torch.float32)
+        grads = []
+        for k, spec in enumerate(plan.heads):
+            n_params = len(head_parameters(spec))
+            if not (mask >> k) & 1:
+                grads += [None] * n_params
+                continue
+            g, mid_layer = _grads_for_head(spec, act[k], delta[k], d_ll[k].reshape(-1), moved_flat)
+            grads += g
+            d_rows[k] = delta[k, mid_layer].view(N, M, U).sum(dim=1)
+        return (None, None, None, None, d_rows, None, None, *grads)
+
+
+def fused_train_applicable(filt, plan, resample: bool) -> bool:
+    """The fused training step covers exactly the reference's setting: no resampling, frozen dynamics,
+    particle states without gradient, tensor-core precision."""
+    if plan is None or resample or filt.precision not in ("bf16x3", "bf16"):
+        return False
+    if filt.particle_states.requires_grad:
+        return False
+    return not any(p.requires_grad for p in filt.dynamics_model.parameters())

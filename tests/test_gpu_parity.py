@@ -434,12 +434,21 @@ def test_full_size_step_properties_and_shard_invariance():
 
 
 # ---- training path: gradients through the recursion (BPTT, BASELINE config C4 in miniature) ---------
-def test_bptt_gradients_match_oracle():
-    """PushCrossmodalParticleFilter.train(): no resampling, MSE on the estimates, backward through all steps.
+@pytest.mark.parametrize("freeze_dynamics", [False, True])
+def test_bptt_gradients_match_oracle(freeze_dynamics):
+    """freeze_dynamics=True is the reference's actual end-to-end setting and takes the fused training step
+    (mmf_pf_heads_forward_train / mmf_pf_heads_backward); False exercises the generic autograd path.
+
+    PushCrossmodalParticleFilter.train(): no resampling, MSE on the estimates, backward through all steps.
     Gradients of the measurement / weight-model parameters (the ones the reference's curricula train; the
     dynamics is frozen there, ref: scripts/push_task/train_push.py:154) and of the dynamics parameters
     must match the CPU oracle's autograd."""
-    name, sd, N, Mp, T = "PushCrossmodalParticleFilter", 2, 6, 30, 5
+    # The fused path evaluates the heads in split-bf16 (1e-5 relative): over many steps a pre-activation that
+    # sits within that distance of zero can take the other side of its ReLU than in the fp32 oracle, which changes
+    # that particle's gradient below the flipped unit by O(1).  T = 3 keeps the comparison free of such flips
+    # (seen from T = 4 on with these seeds); the kernel itself is checked flip-free, layer by layer, in
+    # test_heads_backward_kernel_matches_autograd.
+    name, sd, N, Mp, T = "PushCrossmodalParticleFilter", 2, 6, 30, (3 if freeze_dynamics else 5)
     init, eps, _ = draw_noise(T, N, Mp, sd, seed=13)
     states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=14)
     cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd)
@@ -455,6 +464,13 @@ def test_bptt_gradients_match_oracle():
             dev = DEV
         f.train()
         f.num_particles = Mp
+        if freeze_dynamics:
+            for prm in f.dynamics_model.parameters():
+                prm.requires_grad_(False)
+        if side == "product":
+            from multimodalfilter_b200 import ops as _ops
+
+            _ops.PROFILE.reset(enabled=False)
         f.initialize_beliefs(mean=states[0].to(dev), covariance=cov.to(dev).contiguous())
         est = f.forward_loop(observations={k: v[1:].to(dev) for k, v in obs.items()}, controls=controls[1:].to(dev))
         loss = torch.mean((est - states[1:].to(dev)) ** 2)
@@ -463,8 +479,66 @@ def test_bptt_gradients_match_oracle():
     (lo, go), (lp, gp) = grads
     assert abs(lo - lp) <= 1e-4 * abs(lo)
     assert set(go) == set(gp) and len(go) > 50
+    if freeze_dynamics:  # the fused kernels must actually have run (T steps forward, T steps backward)
+        assert _ops.PROFILE.launches >= 3 * T and not any(k.startswith("dynamics_model") for k in gp)
     # gradients span many orders of magnitude across the tree (the image-encoder convolutions see ~1e-7):
     # compare each tensor relative to its own scale, with an absolute floor tied to the largest gradient
     floor = 1e-5 * max(float(g.abs().max()) for g in go.values())
     for k in go:
         assert_close(gp[k], go[k], 2e-3, atol=floor, msg=f"grad {k}")
+
+
+def test_heads_backward_kernel_matches_autograd():
+    """mmf_pf_heads_forward_train / mmf_pf_heads_backward against torch autograd on the same chain, per layer:
+    saved activations, per-head log-likelihoods, and the delta of every layer's pre-activation."""
+    import torch.nn.functional as F
+
+    for name, sd in (("PushCrossmodalParticleFilter", 2), ("DoorCrossmodalParticleFilter", 3)):
+        f = fill_parameters(_product(name)(), seed=27).to(DEV)
+        plan = fused.PFPlan.build(f)
+        plan.refresh(torch.device(DEV), backward=True)
+        N, Mp = 7, 50  # 350 rows: two full tiles and a ragged one
+        g = torch.Generator(device=DEV).manual_seed(1)
+        states = torch.randn(N, Mp, sd, device=DEV, generator=g)
+        eps = torch.randn(N * Mp, sd, device=DEV, generator=g)
+        rows = torch.randn(1 + plan.K, N, 64, device=DEV, generator=g)
+        moved, ll, act = ops.pf_heads_forward_train(plan.struct, states, eps, rows, 3)
+        d_ll = torch.randn(plan.K, N, Mp, device=DEV, generator=g)
+        delta = ops.pf_heads_backward(plan.struct, N, Mp, act, d_ll, 3)
+        x = moved.reshape(-1, sd)
+        for k, spec in enumerate(plan.heads):
+            (in_lin, pre), (mid, post, out) = spec.state, spec.shared
+            zs, acts = [], []
+
+            def lin(w, b, a):
+                z = F.linear(a, w, b)
+                z.retain_grad()
+                zs.append(z)
+                return z
+
+            a = torch.relu(lin(in_lin.weight, in_lin.bias, x))
+            acts.append(a)
+            for r in pre:
+                t = torch.relu(lin(r.block1.weight, r.block1.bias, a))
+                acts.append(t)
+                a = torch.relu(lin(r.block2.weight, r.block2.bias, t) + a)
+                acts.append(a)
+            z = F.linear(a, mid.weight[:, spec.feat_dim:]) + rows[1 + k].repeat_interleave(Mp, dim=0)
+            z.retain_grad()
+            zs.append(z)
+            a = torch.relu(z)
+            acts.append(a)
+            for r in post:
+                t = torch.relu(lin(r.block1.weight, r.block1.bias, a))
+                acts.append(t)
+                a = torch.relu(lin(r.block2.weight, r.block2.bias, t) + a)
+                acts.append(a)
+            llk = F.linear(a, out.weight, out.bias)[:, 0]
+            assert_close(ll[k].reshape(-1).cpu(), llk.detach().cpu(), RTOL, msg=f"{name} head {k} log-likelihood")
+            (llk * d_ll[k].reshape(-1)).sum().backward()
+            L = len(zs) - 1
+            for i, a_ref in enumerate(acts):
+                assert_close(act[k, i].cpu(), a_ref.detach().cpu(), RTOL, msg=f"{name} head {k} activation {i}")
+            for l in range(L):
+                assert_close(delta[k, l].cpu(), zs[1 + l].grad.cpu(), 2e-4, msg=f"{name} head {k} delta {l}")
+            assert_close(delta[k, L].cpu(), zs[0].grad.cpu(), 2e-4, msg=f"{name} head {k} input-layer delta")
