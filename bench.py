@@ -40,6 +40,8 @@ WORKLOADS = {
            "Push task crossmodal PF eval (state_dim=2, 30 particles), 32 trajectories x 50 steps"),
     "c2": ("DoorCrossmodalKalmanFilter", 3, 256, 1, 100,
            "Door task crossmodal EKF eval (state_dim=3), 256 trajectories x 100 steps"),
+    "c4": ("PushCrossmodalParticleFilter", 2, 8192, 30, 15,
+           "Push crossmodal PF BPTT training step (fwd+bwd, subsequence 16, 8192 trajectories), gradient allreduce"),
 }
 FLOP_PER_PARTICLE_STEP = {2: 189_824.0, 3: 190_336.0}  # BASELINE.md section 4 (hoisted minimum)
 
@@ -160,6 +162,104 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bptt_arm(args):
+    """BASELINE config C4: one BPTT training step = forward over 15 filter steps + backward + gradient
+    all-reduce + Adam, on N=8192 trajectories x 30 particles per GPU.  The observation encoders are hoisted and
+    frozen (their features are inputs, as in the primary timed region of the eval configs): at this batch size
+    the CNN activations a backward through them would have to keep do not fit any GPU (3 encoders x 8192 x 15
+    images x ~0.6 MB).  Trainable: both measurement heads, the observation halves of their first shared Linear,
+    and the modality weight model's fusion layers; the dynamics is frozen as in the reference's curricula."""
+    import torch.distributed as dist
+
+    from multimodalfilter_b200 import _lib, ops
+    from multimodalfilter_b200.crossmodal import models as M_
+    from multimodalfilter_b200.distributed import allreduce_gradients, max_over_ranks
+    from multimodalfilter_b200.synthetic import fill_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().mmf_device_check())
+    name, sd, N, Mp, T, cfg = WORKLOADS["c4"]
+    filt = fill_parameters(M_.PushCrossmodalParticleFilter(), seed=0).to(dev)
+    filt.train()
+    filt.num_particles = Mp
+    filt.precision = args.precision or "bf16x3"
+    for p in filt.dynamics_model.parameters():
+        p.requires_grad_(False)
+    mm = filt.measurement_model
+    wm = mm.crossmodal_weight_model
+    trainable = [p for h in mm.measurement_models for p in list(h.state_layers.parameters()) + list(h.shared_layers.parameters())]
+    trainable += list(wm.fusion_layers.parameters())
+    for p in filt.parameters():
+        p.requires_grad_(False)
+    for p in trainable:
+        p.requires_grad_(True)
+    opt = torch.optim.Adam(trainable, lr=1e-4)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    feats = [torch.randn(T, N, 64, device=dev, generator=g), torch.randn(T, N, 128, device=dev, generator=g)]
+    wm_feats = torch.randn(T, N, 192, device=dev, generator=g)
+    controls = torch.randn(T, N, 7, device=dev, generator=g)
+    targets = torch.randn(T, N, sd, device=dev, generator=g)
+    mean0 = torch.randn(N, sd, device=dev, generator=g)
+    cov = (torch.eye(sd, device=dev) * 0.1)[None].expand(N, sd, sd).contiguous()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        filt.initialize_beliefs(mean=mean0, covariance=cov)
+        ests = []
+        for t in range(T):
+            modw = wm.fusion_layers(wm_feats[t])
+            ests.append(filt.forward(observations=None, controls=controls[t], _hoisted=([feats[0][t], feats[1][t]], modw)))
+        loss = torch.mean((torch.stack(ests) - targets) ** 2)
+        loss.backward()
+        allreduce_gradients(filt)
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ops.PROFILE.reset(enabled=True)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        start.record()
+        for _ in range(args.steps):
+            loss = step()
+        stop.record()
+        barrier()
+    prof = ops.PROFILE.collect()
+    ops.PROFILE.reset(enabled=False)
+    ms = max_over_ranks(start.elapsed_time(stop), dev) / args.steps
+    units = N * Mp * T
+    if rank == 0:
+        kern = {k: {"avg_ms": v["avg_ms"], "share": v["total_ms"] / (ms * args.steps)} for k, v in prof["kernels"].items()}
+        line = {
+            "metric": "particle-steps/sec", "value": world * units / (ms / 1e3), "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": filt.precision, "data": "synthetic",
+            "config": {"workload": cfg, "id": "c4", "model": name, "trajectories_per_gpu": N, "particles": Mp,
+                       "filter_steps_per_pass": T, "phases": "forward + backward + grad all-reduce + Adam",
+                       "encoders": "hoisted and frozen (features are inputs)", "final_loss": float(loss)},
+            "clocks": clk.summary(), "gpu_launches": prof["launches"], "kernels": kern,
+            "e2e": {"value": world * units / (ms / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 4, "note": "training step is device-resident; loss scalar read back"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -176,6 +276,8 @@ def main():
 
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload == "c4":
+        return bptt_arm(args)
 
     import torch.distributed as dist
 

@@ -232,6 +232,10 @@ int mmf_pf_heads_forward_train(const mmf_pf_model* model, int32_t N, int32_t M, 
                                int32_t precision, float* ll_out, float* act_out, float* logw_scratch, void* stream);
 int mmf_pf_heads_backward(const mmf_pf_model* model, int32_t N, int32_t M, const float* act, const float* d_ll,
                           uint32_t enabled_mask, float* delta_out, void* stream);
+/* dW_out (K, L, 64, 64) += delta[k][l]^T act[k][l] for the L 64x64 layers of every head (reduction over the
+ * N*M rows, fp32); dW_out must be zero-initialised by the caller (partial tiles are combined atomically). */
+int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, const float* act, const float* delta,
+                              float* dW_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -273,4 +273,11 @@ int mmf_pf_heads_backward(const mmf_pf_model* model, int32_t N, int32_t M, const
   return launch_head_chain_bwd(model, N, M, act, d_ll, enabled_mask & all, delta_out, (cudaStream_t)stream);
 }
 
+int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, const float* act, const float* delta, float* dW_out,
+                              void* stream) {
+  MMF_REQUIRE(K >= 1 && K <= MMF_MAX_HEADS && L >= 1 && rows >= 0, "heads_weight_grads: bad shape K=%d L=%d", K, L);
+  MMF_REQUIRE(rows == 0 || (act && delta && dW_out), "heads_weight_grads: NULL buffer");
+  return launch_heads_dw(K, L, rows, act, delta, dW_out, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -301,3 +301,82 @@ int launch_head_chain_bwd(const mmf_pf_model* model, int N, int M, const float* 
 }
 
 }  // namespace mmf
+
+// ---- weight gradients: dW[k][l] = delta[k][l]^T act[k][l]  (64 x 64, reduction over the N*M rows) ----------------
+// HBM-bound (2 x 256 B per row per layer against 4096 FMAs): a register-tiled fp32 kernel on the CUDA cores keeps
+// up with the memory system, so the reduction is done in full fp32.  Split over row chunks; partial 64x64 tiles
+// are combined with fp32 atomics into the zero-initialised output.
+namespace mmf {
+
+constexpr int DW_ROWS = 32;      // rows staged per iteration
+constexpr int DW_THREADS = 256;  // each thread owns a 4 x 4 block of the 64 x 64 output
+
+__global__ void __launch_bounds__(DW_THREADS) k_heads_dw(const float* __restrict__ act, const float* __restrict__ delta,
+                                                         float* __restrict__ dW, long long P, int planes_per_head,
+                                                         int L, int rows_per_cta) {
+  __shared__ __align__(16) float sa[DW_ROWS][U];
+  __shared__ __align__(16) float sd[DW_ROWS][U];
+  const int layer = blockIdx.y, head = blockIdx.z;
+  const size_t plane = ((size_t)head * planes_per_head + layer) * (size_t)P * U;
+  const float* A = act + plane;
+  const float* D = delta + plane;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta;
+  const long long row1 = row0 + rows_per_cta < P ? row0 + rows_per_cta : P;
+  const int tid = threadIdx.x;
+  const int jo = (tid >> 4) * 4;  // output-feature block (rows of dW)
+  const int io = (tid & 15) * 4;  // input-feature block  (cols of dW)
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+
+  for (long long r = row0; r < row1; r += DW_ROWS) {
+    __syncthreads();
+    // 32 rows x 64 floats = 512 float4 per operand; 256 threads x 2
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * DW_THREADS;  // float4 index
+      const int rr = e >> 4, c4 = e & 15;
+      const bool ok = r + rr < row1;
+      const float4 va = ok ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(r + rr) * U) + c4) : make_float4(0, 0, 0, 0);
+      const float4 vd = ok ? __ldg(reinterpret_cast<const float4*>(D + (size_t)(r + rr) * U) + c4) : make_float4(0, 0, 0, 0);
+      reinterpret_cast<float4*>(&sa[rr][0])[c4] = va;
+      reinterpret_cast<float4*>(&sd[rr][0])[c4] = vd;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < DW_ROWS; ++rr) {
+      const float4 dv = *reinterpret_cast<const float4*>(&sd[rr][jo]);
+      const float4 av = *reinterpret_cast<const float4*>(&sa[rr][io]);
+      const float dj[4] = {dv.x, dv.y, dv.z, dv.w}, ai[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dj[a], ai[b], acc[a][b]);
+    }
+  }
+  float* out = dW + ((size_t)head * L + layer) * U * U;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) atomicAdd(out + (size_t)(jo + a) * U + io + b, acc[a][b]);
+}
+
+int launch_heads_dw(int K, int L, long long P, const float* act, const float* delta, float* dW, cudaStream_t stream) {
+  if (P == 0) return MMF_OK;
+  int dev = 0, sms = 148;
+  MMF_CUDA(cudaGetDevice(&dev));
+  MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // about 4 CTAs per SM in total, whole multiples of the staging depth per CTA
+  long long chunks = ((long long)sms * 4 + (long long)K * L - 1) / ((long long)K * L);
+  long long rows_per_cta = (P + chunks - 1) / chunks;
+  rows_per_cta = ((rows_per_cta + DW_ROWS - 1) / DW_ROWS) * DW_ROWS;
+  chunks = (P + rows_per_cta - 1) / rows_per_cta;
+  dim3 grid((unsigned)chunks, (unsigned)L, (unsigned)K);
+  k_heads_dw<<<grid, DW_THREADS, 0, stream>>>(act, delta, dW, P, L + 1, L, (int)rows_per_cta);
+  MMF_LAUNCH_CHECK("k_heads_dw");
+  return MMF_OK;
+}
+
+}  // namespace mmf

@@ -128,12 +128,24 @@ def pf_heads_backward(model_struct, N, M, act, d_ll, enabled_mask):
     """d_ll (K,N,M) -> delta (K,L+1,N*M,64): plane l = delta of 64x64 layer l, plane L = delta of the input layer."""
     lib = _lib.load()
     act, d_ll = _f32c(act), _f32c(d_ll)
-    delta = torch.zeros_like(act)
+    delta = torch.empty_like(act)  # every plane of every enabled head is fully written by the kernel
     _lib.check(
         PROFILE.run("pf_heads_backward", 1, lib.mmf_pf_heads_backward, C.byref(model_struct), N, M, _lib.ptr(act),
                     _lib.ptr(d_ll), enabled_mask, _lib.ptr(delta), _lib.stream_of(act))
     )
     return delta
+
+
+def pf_heads_weight_grads(act, delta):
+    """act, delta (K, L+1, P, 64) -> dW (K, L, 64, 64) with dW[k, l] = delta[k, l]^T act[k, l]."""
+    lib = _lib.load()
+    K, Lp1, P, _ = act.shape
+    dW = torch.zeros((K, Lp1 - 1, _lib.UNITS, _lib.UNITS), device=act.device, dtype=torch.float32)
+    _lib.check(
+        PROFILE.run("pf_heads_weight_grads", 1, lib.mmf_pf_heads_weight_grads, K, Lp1 - 1, P, _lib.ptr(act),
+                    _lib.ptr(delta), _lib.ptr(dW), _lib.stream_of(act))
+    )
+    return dW
 
 
 def pf_init(mean, covariance, eps_MNsd):

@@ -150,10 +150,10 @@ class ParticleFilter(Filter):
         if plan is not None and not grad and isinstance(controls, torch.Tensor):
             return self._step_fused(plan, observations, controls, mode, _hoisted)
         if grad and isinstance(controls, torch.Tensor) and training.fused_train_applicable(self, plan, resample):
-            return self._step_fused_train(plan, observations, controls)
+            return self._step_fused_train(plan, observations, controls, _hoisted)
         return self._step_generic(observations, controls, resample, mode, grad)
 
-    def _step_fused_train(self, plan, observations, controls):
+    def _step_fused_train(self, plan, observations, controls, hoisted=None):
         """BPTT step (train mode: no resampling; dynamics frozen): kernels for the per-particle work, torch
         ops with autograd for the (N, M)-sized fusion / normalisation / estimate and the per-trajectory modules."""
         states, logw = self.particle_states, self.particle_log_weights
@@ -169,13 +169,13 @@ class ParticleFilter(Filter):
                 rows.append(states.new_zeros((N, fused.U)))
                 continue
             mid = spec.shared[0]
-            feats = spec.observation_features(observations)
+            feats = spec.observation_features(observations) if hoisted is None else hoisted[0][len(rows)]
             rows.append(torch.nn.functional.linear(feats, mid.weight[:, : spec.feat_dim], mid.bias))
         eps = self._process_eps(N * M, sd, states)
         moved, ll = training.FusedHeads.apply(plan, states, eps, dyn_row, torch.stack(rows), plan.enabled_mask(),
                                              ops.PRECISIONS[self.precision], *params)
         ll = ll[[k for k, on in enumerate(enabled) if on]].permute(1, 2, 0)  # (N, M, K_enabled)
-        modw = plan.modality_log_weights(observations)
+        modw = plan.modality_log_weights(observations) if hoisted is None else hoisted[1]
         if modw is not None:
             ll = ll + modw[:, enabled][:, None, :]
         logw_unnorm = logw + torch.logsumexp(ll, dim=2)

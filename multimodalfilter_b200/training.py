@@ -36,26 +36,26 @@ def head_parameters(spec) -> List[torch.Tensor]:
     return ps
 
 
-def _grads_for_head(spec, act, delta, d_ll, moved_flat):
-    """act/delta: (L+1, P, 64); d_ll: (P,); moved_flat: (P, sd).  Returns grads in head_parameters order."""
+def _grads_for_head(spec, act, delta, dW, d_ll, moved_flat):
+    """act/delta: (L+1, P, 64); dW: (L, 64, 64) from mmf_pf_heads_weight_grads; d_ll: (P,); moved_flat: (P, sd).
+    Returns grads in head_parameters order."""
     (in_lin, pre), (mid, post, out) = spec.state, spec.shared
     L = 2 * len(pre) + 1 + 2 * len(post)
-    grads = []
-    d_in = delta[L]
-    grads += [d_in.t() @ moved_flat, d_in.sum(0)]
+    db = delta.sum(dim=1)  # (L+1, 64)
+    grads = [delta[L].t() @ moved_flat, db[L]]
     layer = 0
     for _ in pre:
         for _half in range(2):
-            grads += [delta[layer].t() @ act[layer], delta[layer].sum(0)]
+            grads += [dW[layer], db[layer]]
             layer += 1
     g_mid = torch.zeros_like(mid.weight)
-    g_mid[:, spec.feat_dim:] = delta[layer].t() @ act[layer]  # state half; the observation half flows through the rows
+    g_mid[:, spec.feat_dim:] = dW[layer]  # state half; the observation half flows through the rows
     grads += [g_mid]
     mid_layer = layer
     layer += 1
     for _ in post:
         for _half in range(2):
-            grads += [delta[layer].t() @ act[layer], delta[layer].sum(0)]
+            grads += [dW[layer], db[layer]]
             layer += 1
     grads += [(d_ll[None, :] @ act[L]), d_ll.sum().reshape(1)]
     return grads, mid_layer
@@ -84,6 +84,12 @@ class FusedHeads(torch.autograd.Function):
         act, moved = ctx.saved_tensors
         d_ll = torch.nan_to_num(d_ll.contiguous(), nan=0.0)
         delta = ops.pf_heads_backward(plan.struct, N, M, act, d_ll, mask)
+        if mask != (1 << plan.K) - 1:  # planes of disabled heads are never written by the kernels
+            for k in range(plan.K):
+                if not (mask >> k) & 1:
+                    delta[k].zero_()
+                    act[k].zero_()
+        dW = ops.pf_heads_weight_grads(act, delta)
         moved_flat = moved.reshape(N * M, sd)
         d_rows = torch.zeros((plan.K, N, U), device=act.device, dtype=torch.float32)
         grads = []
@@ -92,7 +98,7 @@ class FusedHeads(torch.autograd.Function):
             if not (mask >> k) & 1:
                 grads += [None] * n_params
                 continue
-            g, mid_layer = _grads_for_head(spec, act[k], delta[k], d_ll[k].reshape(-1), moved_flat)
+            g, mid_layer = _grads_for_head(spec, act[k], delta[k], dW[k], d_ll[k].reshape(-1), moved_flat)
             grads += g
             d_rows[k] = delta[k, mid_layer].view(N, M, U).sum(dim=1)
         return (None, None, None, None, d_rows, None, None, *grads)
