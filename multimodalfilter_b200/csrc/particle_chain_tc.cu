@@ -485,6 +485,341 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
   }
 }
 
+
+// ---- pipelined variant (MMF_TC_VARIANT=51) ------------------------------------------------------------------
+// Same tiles, same arithmetic per layer, different hand-over between the CUDA cores and the tensor pipe:
+//   * every group has a dedicated issuer warp (warp 4*G + g) that issues its tcgen05.mma; the 128 threads of a
+//     group never meet at a barrier, they only arrive on mbarriers;
+//   * the next A operand is written IN PLACE over the accumulator chunk it was computed from (16 fp32 columns ->
+//     8 columns of bf16x2 hi + 8 columns of lo) and the accumulator ping-pongs between the two 64-column halves
+//     of the group's TMEM slice, so K step k of layer l+1 is issued as soon as chunk k of layer l's epilogue is
+//     done, while the group is still working on chunks k+1...: the group's serial chain per layer shrinks from
+//     "epilogue + 12 MMAs + commit latency" to "epilogue + 3 MMAs + commit latency".
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// publish chunk `chunk` of the A operand: stores retired -> ordered before the arrive the issuer observes
+__device__ __forceinline__ void publish_chunk(uint64_t* cbar, int chunk) {
+  tc_wait_st();
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(cbar + chunk);  // one arrival per warp: 128 lanes on one mbarrier serialise
+}
+
+// tbuf / bias4 / act_row / cbar already point at this thread's first column (chunk); NCH chunks of 16 columns
+template <int KIND, int NCH>
+__device__ __forceinline__ void epilogue_pipe(uint32_t tbuf, const float4* __restrict__ bias4, float2 (&xr)[NCH * 8],
+                                              bool single_pass, float* act_row, uint64_t* cbar) {
+  uint32_t d[2][16];
+  tmem_ld16(tbuf, d[0]);
+  tc_wait_ld();
+#pragma unroll
+  for (int chunk = 0; chunk < NCH; ++chunk) {
+    if (chunk + 1 < NCH) tmem_ld16(tbuf + (chunk + 1) * 16, d[(chunk + 1) & 1]);
+    float2 b[8];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 t = (KIND >= EPI_MID_RELU) ? __ldg(bias4 + chunk * 4 + q4) : bias4[chunk * 4 + q4];
+      b[2 * q4] = make_float2(t.x, t.y);
+      b[2 * q4 + 1] = make_float2(t.z, t.w);
+    }
+    float2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 a = __fadd2_rn(make_float2(__uint_as_float(d[chunk & 1][2 * j]), __uint_as_float(d[chunk & 1][2 * j + 1])), b[j]);
+      if (KIND == EPI_RES_B) a = __fadd2_rn(a, xr[chunk * 8 + j]);
+      if (KIND == EPI_RES_B || KIND == EPI_MID_RELU) {
+        a.x = fmaxf(a.x, 0.0f);
+        a.y = fmaxf(a.y, 0.0f);
+      }
+      if (KIND != EPI_RES_A) xr[chunk * 8 + j] = a;
+      v[j] = a;
+    }
+    if (act_row != nullptr) {
+      if (KIND == EPI_RES_A) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = make_float2(fmaxf(v[j].x, 0.0f), fmaxf(v[j].y, 0.0f));
+      }
+      store_act_chunk(act_row, chunk, v);
+    }
+    // in place: hi -> columns [16 chunk, +8), lo -> [16 chunk + 8, +8) of the buffer just read
+    // chunk-1's stores have had this chunk's arithmetic to retire: publish it now, then store this chunk
+    if (chunk > 0) publish_chunk(cbar, chunk - 1);
+    if (KIND == EPI_RES_A) store_a_chunk<true>(v, tbuf + chunk * 8, tbuf + chunk * 8 + 8, chunk, single_pass);
+    else store_a_chunk<false>(v, tbuf + chunk * 8, tbuf + chunk * 8 + 8, chunk, single_pass);
+    if (chunk + 1 < NCH) tc_wait_ld();
+  }
+  publish_chunk(cbar, NCH - 1);
+}
+
+// number of tiles group g of CTA `unit` processes (tile = (it * units + unit) * G + g < tiles)
+__device__ __forceinline__ long long group_tile_count(long long tiles, int G, int g, long long unit, long long units) {
+  const long long slots = tiles > g ? (tiles - g + G - 1) / G : 0;
+  return slots > unit ? (slots - unit + units - 1) / units : 0;
+}
+
+// TPR = threads per particle row: 1 -> a thread owns all 64 columns of its row; 2 -> two warps share a TMEM lane
+// quadrant and own 32 columns each (twice the warps per scheduler to hide the TMEM / conversion latencies).
+template <int TC_GROUPS, int TPR>
+__global__ void __launch_bounds__(TC_GROUPS * (128 * TPR + 32), 1) k_particle_chain_pipe(const __grid_constant__ TcParams P) {
+  constexpr int CH = U / 16;
+  constexpr int NCH = CH / TPR;       // chunks per thread
+  constexpr int WPG = 4 * TPR;        // worker warps per group
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + P.image_cap);
+  uint64_t* done = wbar + 1;                 // accumulator complete, one per group (tcgen05.commit)
+  uint64_t* cbar = done + TC_MAX_GROUPS;     // A chunk ready, [group][chunk], one arrival per warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cbar + TC_MAX_GROUPS * CH);
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const bool issuer = warp >= TC_GROUPS * WPG;  // warp G*WPG + i issues the MMAs of group i
+  const int g = issuer ? warp - TC_GROUPS * WPG : warp / WPG;
+  const int wig = warp - g * WPG;               // worker: warp inside the group
+  const int quad = wig & 3;                     // TMEM lane quadrant
+  const int half = wig >> 2;                    // which NCH chunks of the row this thread owns
+  const int row = quad * 32 + (tid & 31);
+  const int col0 = half * NCH * 16;
+  const int sd = P.sd;
+  const bool single_pass = P.single_pass != 0;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int i = 0; i < TC_GROUPS; ++i) {
+      mbar_init(done + i, 1);
+      for (int k = 0; k < CH; ++k) mbar_init(cbar + i * CH + k, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+  const uint32_t tG = tmem_base + g * 128 + lane_off;  // this thread's view of its group's slice
+  uint32_t wphase = 0;
+  // batches[g] = MMA batches (layers) group g has been through so far; its parity is at once the phase of the
+  // group's mbarriers and the half of the slice that holds the A operand.  Workers track their own group.
+  long long batches = 0;
+  uint32_t cur = 0, dphase = 0;
+
+  const long long tiles = (P.total + 127) / 128;
+  constexpr uint32_t IDESC_L = make_idesc(64, 128);
+  constexpr uint32_t IDESC_O = make_idesc(OUT_PAD, 128);
+  const long long unit = blockIdx.x, units = gridDim.x;
+
+  for (int c = P.first_chain; c <= P.K; ++c) {
+    if (c > 0 && !((P.enabled >> (c - 1)) & 1u)) continue;
+    const ChainDev ch = P.chains[c];
+    const int L = chain_layers(ch);
+    bool last_head = false, first_head = false;
+    if (c > 0) {
+      last_head = (P.enabled >> c) == 0;
+      first_head = (P.enabled & ((1u << (c - 1)) - 1u)) == 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)image_bytes(ch, 1);
+      const uint8_t* src = P.images[c];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(wbar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768) {
+        const uint32_t n = bytes - off < 32768 ? bytes - off : 32768;
+        bulk_g2s(smem + off, src + off, n, wbar);
+      }
+    }
+    mbar_wait(wbar, wphase);
+    wphase ^= 1;
+    const uint32_t tiles_addr = smem_u32(smem);
+
+    if (issuer) {
+      // ------------------------------------------------------------------------------- issuer warp of group g
+      const long long my_tiles = group_tile_count(tiles, TC_GROUPS, g, unit, units);
+      if (elect_one_sync()) {
+        const uint32_t slice = tmem_base + g * 128;
+        uint64_t* my_cbar = cbar + g * CH;
+        uint32_t par = (uint32_t)(batches & 1);
+        for (long long t = 0; t < my_tiles; ++t) {
+          for (int layer = 0; layer <= L; ++layer) {
+            const bool is_out = layer == L;
+            const uint32_t hi_addr = tiles_addr + (is_out ? (uint32_t)L * 2 * TILE_B : (uint32_t)layer * 2 * TILE_B);
+            const uint32_t lo_addr = hi_addr + (is_out ? OUT_TILE_B : TILE_B);
+            const uint64_t bhi = make_b_desc(hi_addr), blo = make_b_desc(lo_addr);
+            const uint32_t idesc = is_out ? IDESC_O : IDESC_L;
+            const uint32_t abuf = slice + par * 64, dbuf = slice + (par ^ 1u) * 64;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+              mbar_wait(my_cbar + k, par);
+              tc_fence_after();
+              mma_ts(dbuf, abuf + k * 16, bhi + (uint64_t)(k * 2), idesc, k > 0);
+              if (!single_pass) {
+                mma_ts(dbuf, abuf + k * 16, blo + (uint64_t)(k * 2), idesc, 1);
+                mma_ts(dbuf, abuf + k * 16 + 8, bhi + (uint64_t)(k * 2), idesc, 1);
+              }
+            }
+            tc_commit(done + g);
+            par ^= 1u;
+          }
+        }
+      }
+      __syncwarp();
+      batches += my_tiles * (L + 1);
+      continue;
+    }
+
+    // ---------------------------------------------------------------------------------------------- worker groups
+    const float* fsm = reinterpret_cast<const float*>(smem + image_tiles_bytes(ch, 1));
+    const float* in_Wt = fsm;
+    const float* in_b = fsm + ch.in_dim * U;
+    const float* biases = in_b + U;
+    const float* out_b = biases + L * U;
+    const int mid_at = 2 * ch.n_pre;
+    uint64_t* my_cbar = cbar + g * CH + half * NCH;
+
+    for (long long it = 0;; ++it) {
+      const long long tile = (it * units + unit) * TC_GROUPS + g;
+      if (tile >= tiles) break;
+      const long long p_raw = tile * 128 + row;
+      const bool live = p_raw < P.total;
+      const long long p = live ? p_raw : P.total - 1;
+      const int n = (int)(p / P.M);
+      const float* xsrc = (c == 0) ? P.states_in : P.states_out;
+      float x[MMF_MAX_SD];
+#pragma unroll
+      for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
+      float* act_base = (P.act_out != nullptr && c > 0 && live)
+                            ? P.act_out + ((size_t)(c - 1) * (L + 1) * P.total + (size_t)p) * U
+                            : nullptr;
+      const size_t act_plane = (size_t)P.total * U;
+
+      // input layer on the CUDA cores -> A operand in the current half, published chunk by chunk
+      float2 xr[NCH * 8];
+      {
+        const uint32_t tbuf = tG + cur * 64 + col0;
+        const float4* b4 = reinterpret_cast<const float4*>(in_b + col0);
+        const float4* w4 = reinterpret_cast<const float4*>(in_Wt + col0);
+        float* act0 = act_base ? act_base + col0 : nullptr;
+#pragma unroll
+        for (int chunk = 0; chunk < NCH; ++chunk) {
+          float2 v[8];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 t = b4[chunk * 4 + q4];
+            v[2 * q4] = make_float2(t.x, t.y);
+            v[2 * q4 + 1] = make_float2(t.z, t.w);
+          }
+#pragma unroll
+          for (int i = 0; i < MMF_MAX_SD; ++i) {
+            if (i < sd) {
+              const float2 xi = make_float2(x[i], x[i]);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 t = w4[i * (U / 4) + chunk * 4 + q4];
+                v[2 * q4] = __ffma2_rn(make_float2(t.x, t.y), xi, v[2 * q4]);
+                v[2 * q4 + 1] = __ffma2_rn(make_float2(t.z, t.w), xi, v[2 * q4 + 1]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j].x = fmaxf(v[j].x, 0.0f);
+            v[j].y = fmaxf(v[j].y, 0.0f);
+            xr[chunk * 8 + j] = v[j];
+          }
+          if (act0 != nullptr) store_act_chunk(act0, chunk, v);
+          if (chunk > 0) publish_chunk(my_cbar, chunk - 1);
+          store_a_chunk<false>(v, tbuf + chunk * 8, tbuf + chunk * 8 + 8, chunk, single_pass);
+        }
+        publish_chunk(my_cbar, NCH - 1);
+      }
+
+      for (int layer = 0; layer <= L; ++layer) {
+        mbar_wait(done + g, dphase, P.wait_hint_ns);
+        dphase ^= 1;
+        cur ^= 1;
+        tc_fence_after();
+        if (layer == L) break;
+        const uint32_t tbuf = tG + cur * 64 + col0;
+        float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane + col0 : nullptr;
+        if (layer == mid_at) {
+          const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U + col0);
+          if (ch.mid_relu) epilogue_pipe<EPI_MID_RELU, NCH>(tbuf, brow, xr, single_pass, arow, my_cbar);
+          else epilogue_pipe<EPI_MID_LINEAR, NCH>(tbuf, brow, xr, single_pass, arow, my_cbar);
+        } else {
+          const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
+          const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U + col0);
+          if ((rel & 1) == 0) epilogue_pipe<EPI_RES_A, NCH>(tbuf, bsm, xr, single_pass, arow, my_cbar);
+          else epilogue_pipe<EPI_RES_B, NCH>(tbuf, bsm, xr, single_pass, arow, my_cbar);
+        }
+      }
+
+      if (half != 0) continue;  // the second warp of a row pair has no part in the 16-column output layer
+      float y[MMF_MAX_SD + 1];
+      {
+        uint32_t d[16];
+        tmem_ld16(tG + cur * 64, d);
+        tc_wait_ld();
+#pragma unroll
+        for (int o = 0; o < MMF_MAX_SD + 1; ++o) y[o] = __uint_as_float(d[o]) + out_b[o];
+      }
+      if (c == 0) {
+        float gsel = 0.0f;
+#pragma unroll
+        for (int o = 0; o < MMF_MAX_SD + 1; ++o)
+          if (o == sd) gsel = y[o];
+        const float gate = 1.0f / (1.0f + expf(-gsel));
+        float e[MMF_MAX_SD];
+#pragma unroll
+        for (int i = 0; i < MMF_MAX_SD; ++i) e[i] = (i < sd) ? P.eps[p * sd + i] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < MMF_MAX_SD; ++i) {
+          if (i < sd) {
+            float noise = 0.0f;
+#pragma unroll
+            for (int j = 0; j < MMF_MAX_SD; ++j)
+              if (j <= i && j < sd) noise = fmaf(P.q[i * sd + j], e[j], noise);
+            const float moved = (x[i] + y[i] * gate) + noise;
+            if (live) P.states_out[p * sd + i] = moved;
+          }
+        }
+      } else {
+        const float ll = y[0];
+        if (P.ll_out != nullptr && live) P.ll_out[(size_t)(c - 1) * P.total + p] = ll;
+        const float v = ll + (P.modw != nullptr ? __ldg(P.modw + (size_t)n * P.K + (c - 1)) : 0.0f);
+        float fused = v;
+        if (!first_head) {
+          const float prev = P.logw_out[p];
+          const float mx = fmaxf(prev, v);
+          fused = (mx == -INFINITY) ? -INFINITY : mx + logf(expf(prev - mx) + expf(v - mx));
+        }
+        if (live) P.logw_out[p] = last_head ? P.logw_in[p] + fused : fused;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
                              const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
                              int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream,
@@ -563,6 +898,26 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
     cfg.numAttrs = 1;                                                                             \
     MMF_CUDA(cudaLaunchKernelEx(&cfg, k_particle_chain_tc<G, PAIRED>, P));                        \
   } while (0)
+#define MMF_PIPE_LAUNCH(G, TPR)                                                                      \
+  do {                                                                                            \
+    static thread_local int configured_dev = -1;                                                  \
+    static thread_local size_t window = 0;                                                        \
+    if (configured_dev != dev) {                                                                  \
+      int rc = opt_in_shared_memory(k_particle_chain_pipe<G, TPR>, &window);                      \
+      if (rc) return rc;                                                                          \
+      configured_dev = dev;                                                                       \
+    }                                                                                             \
+    MMF_REQUIRE(smem <= window, "tensor-core chain needs %zu B of shared memory (window %zu B)", smem, window); \
+    long long units = (tiles + G - 1) / G;                                                        \
+    if (units > sms) units = sms;                                                                 \
+    k_particle_chain_pipe<G, TPR><<<(unsigned)units, G * (128 * TPR + 32), smem, stream>>>(P); \
+    MMF_LAUNCH_CHECK("k_particle_chain_pipe");                                                    \
+    return MMF_OK;                                                                                \
+  } while (0)
+  if (variant == 51) MMF_PIPE_LAUNCH(4, 1);
+  if (variant == 53) MMF_PIPE_LAUNCH(3, 1);
+  if (variant == 63) MMF_PIPE_LAUNCH(3, 2);
+#undef MMF_PIPE_LAUNCH
   switch (variant) {
     case 41: MMF_TC_LAUNCH(4, false); break;
     case 31: MMF_TC_LAUNCH(3, false); break;

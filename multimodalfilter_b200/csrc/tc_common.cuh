@@ -189,25 +189,31 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int m = 128) {
 }
 
 // bf16 split of 8 fp32 pairs, stored as the next A operand (columns [8*chunk, 8*chunk+8) of the hi and lo
-// regions):  hi = rz_bf16(v) (truncation == the top 16 bits of v), lo = rn_bf16(v - hi).  With RELU the
-// activation is folded into the two conversions: v < 0 gives hi = 0, and v - trunc(v) <= 0 gives lo = 0,
-// so no separate max() is needed.  5 instructions per pair: F2FP, 2 x LOP, FFMA2, F2FP.
+// regions):  hi = rz_bf16(v) (truncation == the top 16 bits of v), lo = rn_bf16(v - hi); v - hi is exact.
+// The remainder is formed by the mixed-precision FMA (PTX fma.rn.f32.bf16 -> FHFMA.BF16), which reads the packed
+// bf16 halves in place: 4 instructions per pair (F2FP, 2 x FHFMA, F2FP), only the two conversions on the
+// half-rate ALU pipe (ncu: the ALU pipe was the busiest pipe of the epilogue with the mask-and-subtract form).
+// With RELU the activation is folded into the two conversions: v < 0 gives hi = 0, then v - 0 < 0 gives lo = 0.
 template <bool RELU>
 __device__ __forceinline__ void store_a_chunk(const float2 (&v)[8], uint32_t tAhi, uint32_t tAlo, int chunk,
                                               bool single_pass) {
   uint32_t hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float2 t = make_float2(__uint_as_float(__float_as_uint(v[j].x) & 0xffff0000u),
-                                 __uint_as_float(__float_as_uint(v[j].y) & 0xffff0000u));
-    const float2 r = __ffma2_rn(t, make_float2(-1.0f, -1.0f), v[j]);
-    if (RELU) {
-      asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[j].y), "f"(v[j].x));
-      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(r.y), "f"(r.x));
-    } else {
-      asm("cvt.rz.bf16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[j].y), "f"(v[j].x));
-      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(r.y), "f"(r.x));
-    }
+    if (RELU) asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[j].y), "f"(v[j].x));
+    else asm("cvt.rz.bf16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[j].y), "f"(v[j].x));
+    float rx, ry;
+    asm("{\n\t"
+        ".reg .b16 l, h, m1;\n\t"
+        "mov.b32 {l, h}, %2;\n\t"
+        "mov.b16 m1, 0xBF80;\n\t"  // -1.0 in bf16
+        "fma.rn.f32.bf16 %0, l, m1, %3;\n\t"
+        "fma.rn.f32.bf16 %1, h, m1, %4;\n\t"
+        "}"
+        : "=f"(rx), "=f"(ry)
+        : "r"(hi[j]), "f"(v[j].x), "f"(v[j].y));
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(ry), "f"(rx));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(ry), "f"(rx));
   }
   tmem_st8(tAhi + chunk * 8, hi);
   if (!single_pass) tmem_st8(tAlo + chunk * 8, lo);

@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int batches, int reps, unsign
   __syncthreads();
   tc_fence_after();
   const uint32_t base = slot;
-  if (tid == 0) {
+  uint32_t elected = 0;
+  if (warp == 0)
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+  if (elected) {
     const uint64_t b0 = make_b_desc(smem_u32(smem));
     const uint32_t id = idesc(N);
     uint32_t phase = 0;
