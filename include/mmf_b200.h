@@ -232,6 +232,22 @@ int mmf_pf_heads_forward_train(const mmf_pf_model* model, int32_t N, int32_t M, 
                                int32_t precision, float* ll_out, float* act_out, float* logw_scratch, void* stream);
 int mmf_pf_heads_backward(const mmf_pf_model* model, int32_t N, int32_t M, const float* act, const float* d_ll,
                           uint32_t enabled_mask, float* delta_out, void* stream);
+/* ---- image observation encoder: convolutional trunk ------------------------------------
+ * Replaces the Conv2d layers of observation_image_layers (ref: crossmodal/push_models/layers.py:93-101,
+ * crossmodal/door_models/layers.py:43-57) for 32x32 single-channel images.  Activation maps are bf16 hi/lo
+ * planes, mmf_enc_map_bytes(channels) bytes per image, and MUST be zero-initialised once by the caller (the
+ * kernels rely on zero guard regions they never write).
+ *   mmf_enc_stem      Conv2d(1, 32, 5, padding=2) + ReLU; w = weight as [tap 25][32] then bias[32], fp32.
+ *   mmf_enc_conv3x3   Conv2d(cin, cout, 3, padding=1) [+ residual map] [+ ReLU] on the tensor cores
+ *                     (bf16 hi/lo split operands, fp32 accumulation); (cin, cout) in {(32,32), (32,16), (16,<=16)}.
+ *                     w_image = bf16 [hi|lo][tap 9][cin/8][npad][8] then fp32 bias[npad], npad = 32 if cout > 16
+ *                     else 16 (rows >= cout zero).  Writes out_map (planes, npad channels) and/or out_nchw
+ *                     (n_images, cout, 32, 32) fp32. */
+size_t mmf_enc_map_bytes(int32_t channels);
+int mmf_enc_stem(int32_t n_images, const float* images, const float* w, void* out_map, void* stream);
+int mmf_enc_conv3x3(int32_t n_images, int32_t cin, int32_t cout, const void* in_map, const void* w_image,
+                    const void* res_map, int32_t relu, void* out_map, float* out_nchw, void* stream);
+
 /* dW_out (K, L, 64, 64) += delta[k][l]^T act[k][l] for the L 64x64 layers of every head (reduction over the
  * N*M rows, fp32); dW_out must be zero-initialised by the caller (partial tiles are combined atomically). */
 int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, const float* act, const float* delta,

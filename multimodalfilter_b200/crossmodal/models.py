@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from .. import fused, ops
+from ..encoders import ImageEncoder
 from ..fannypack.nn import resblocks
 from ..fannypack.utils import SliceWrapper
 from ..torchfilter import base as tf_base
@@ -54,7 +55,7 @@ def _image_encoder(units: int, spanning_avg_pool: bool = False) -> nn.Sequential
     else:
         layers += [nn.Conv2d(16, 8, 3, padding=1), nn.Flatten(), nn.Linear(8 * 32 * 32, units)]
     layers += [nn.ReLU(inplace=True), resblocks.Linear(units)]
-    return nn.Sequential(*layers)
+    return ImageEncoder(*layers)
 
 
 class _Encoders(nn.Module):

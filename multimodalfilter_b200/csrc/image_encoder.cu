@@ -1,0 +1,384 @@
+// image_encoder.cu -- the convolutional trunk of the image observation encoder:
+//   Conv2d(1,32,5,p=2) ReLU | resblock Conv2d(32,k=3) | Conv2d(32,16,3,p=1) ReLU | Conv2d(16,8,3,p=1)
+// (ref: crossmodal/push_models/layers.py:93-104, crossmodal/door_models/layers.py:43-63), 32x32 images.
+// The encoders are state independent, so the host runs them once over all T*N images of a sequence
+// (fused.batched_over_time); at BASELINE config C3 that is 409,600 images = 21 TFLOP of fp32 convolution, which
+// dominates the end-to-end forward_loop time when left to the library's fp32 path.
+//
+// Here every 3x3 convolution is an implicit GEMM on the tensor cores with fp32-grade accuracy:
+//   * activations live in HBM as bf16 hi/lo PLANES: map[image][channel chunk of 8][hi|lo][position][8 ch], a
+//     position being y * 34 + x (row pitch 34 = 32 pixels + 2 zero pad columns) behind a 64-position zero guard,
+//     so the neighbour (dy, dx) of position p is simply position p + 34 dy + dx and the zero padding of the
+//     convolution is data, not control flow;
+//   * a tile is 128 consecutive positions (9 tiles per image); its input window (208 positions per plane) is
+//     brought into shared memory by bulk async copies (TMA), and the A operand of tap (dy, dx) is that same
+//     shared memory addressed through a no-swizzle K-major UMMA descriptor whose start address is shifted by
+//     34 dy + dx positions: no im2col, no gather instructions at all;
+//   * D[128 positions x Cout] += A_tap[128 x Cin] * W_tap[Cin x Cout] for the 9 taps, three bf16 MMAs per K
+//     step (hi*hi + lo*hi + hi*lo), accumulated in TMEM in fp32;
+//   * warp-specialised pipeline: warp 0 = TMA producer, warp 1 = MMA issuer, warps 4-11 = two epilogue groups
+//     (bias, residual, ReLU, bf16 split, coalesced 16-byte plane stores), 4 stages of shared memory / TMEM.
+// The 5x5 stem (one input channel, 1.6 MFLOP per image) runs on the CUDA cores and emits the first map.
+#include "tc_common.cuh"
+
+namespace mmf {
+
+constexpr int ENC_PITCH = 34;                 // positions per image row (32 pixels + 2 zero pads)
+constexpr int ENC_NPOS = 32 * ENC_PITCH;      // 1088 positions hold an image
+constexpr int ENC_TILES = 9;                  // 9 x 128 = 1152 >= 1088
+constexpr int ENC_GUARD = 64;                 // zero positions in front of position 0
+constexpr int ENC_PLANE_POS = ENC_GUARD + ENC_TILES * 128 + 64;  // 1280
+constexpr int ENC_PLANE_B = ENC_PLANE_POS * 16;                  // bytes of one (chunk, hi|lo) plane
+constexpr int ENC_HALO = 40;                  // >= 35 = pitch + 1, multiple of 8
+constexpr int ENC_WIN_POS = 128 + 2 * ENC_HALO;  // 208 positions per plane in a stage
+constexpr int ENC_WIN_B = ENC_WIN_POS * 16;      // 3328 B
+constexpr int ENC_STAGES = 4;
+constexpr int ENC_THREADS = 384;
+
+__host__ __device__ inline size_t enc_map_bytes(int channels) { return (size_t)(channels / 8) * 2 * ENC_PLANE_B; }
+
+// no-swizzle K-major shared-memory matrix descriptor: rows of 16 bytes, 8 consecutive rows = one core matrix,
+// SBO = distance between 8-row groups, LBO = distance between the two 16-byte K chunks of one K = 16 step.
+__device__ __forceinline__ uint64_t make_desc_interleave(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// bf16 hi/lo split of 8 channels -> two 16-byte plane elements: hi = rn_bf16(v), lo = rn_bf16(v - hi) (v - hi is
+// exact), so hi + lo carries v to 2^-18 relative; the remainder uses the mixed-precision FMA like store_a_chunk
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi4, uint4& lo4) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+    float rx, ry;
+    asm("{\n\t"
+        ".reg .b16 l, h, m1;\n\t"
+        "mov.b32 {l, h}, %2;\n\t"
+        "mov.b16 m1, 0xBF80;\n\t"
+        "fma.rn.f32.bf16 %0, l, m1, %3;\n\t"
+        "fma.rn.f32.bf16 %1, h, m1, %4;\n\t"
+        "}"
+        : "=f"(rx), "=f"(ry)
+        : "r"(hi[j]), "f"(v[2 * j]), "f"(v[2 * j + 1]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(ry), "f"(rx));
+  }
+  hi4 = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  lo4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void unpack8(const uint4& hi4, const uint4& lo4, float (&v)[8]) {
+  const uint32_t h[4] = {hi4.x, hi4.y, hi4.z, hi4.w}, l[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(h[j] << 16) + __uint_as_float(l[j] << 16);
+    v[2 * j + 1] = __uint_as_float(h[j] & 0xffff0000u) + __uint_as_float(l[j] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ bool enc_valid(int pos) { return pos < ENC_NPOS && (pos % ENC_PITCH) < 32; }
+
+// ---- 5x5 stem on the CUDA cores: image (32x32 fp32) -> 32-channel map, ReLU --------------------------------
+// weights: w[25][32] (tap-major) then bias[32], fp32.
+__global__ void __launch_bounds__(256) k_enc_stem(const float* __restrict__ images, const float* __restrict__ w,
+                                                  uint8_t* __restrict__ out_map, int n_images) {
+  __shared__ float img[36 * 36];
+  __shared__ __align__(16) float ws[25 * 32 + 32];
+  for (int i = threadIdx.x; i < 25 * 32 + 32; i += blockDim.x) ws[i] = w[i];
+  for (int image = blockIdx.x; image < n_images; image += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 36 * 36; i += blockDim.x) {
+      const int y = i / 36 - 2, x = i % 36 - 2;
+      img[i] = (y >= 0 && y < 32 && x >= 0 && x < 32) ? images[(size_t)image * 1024 + y * 32 + x] : 0.0f;
+    }
+    __syncthreads();
+    uint8_t* map = out_map + (size_t)image * enc_map_bytes(32);
+    for (int pos = threadIdx.x; pos < ENC_TILES * 128; pos += blockDim.x) {
+      const bool valid = enc_valid(pos);
+      float acc[32];
+      if (valid) {
+        const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = ws[25 * 32 + c];
+        for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const float p = img[(y + ky) * 36 + x + kx];
+            const float4* w4 = reinterpret_cast<const float4*>(ws + (ky * 5 + kx) * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = w4[q];
+              acc[4 * q] = fmaf(t.x, p, acc[4 * q]);
+              acc[4 * q + 1] = fmaf(t.y, p, acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(t.z, p, acc[4 * q + 2]);
+              acc[4 * q + 3] = fmaf(t.w, p, acc[4 * q + 3]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = valid ? fmaxf(acc[kc * 8 + j], 0.0f) : 0.0f;
+        uint4 hi4, lo4;
+        split8(v, hi4, lo4);
+        uint8_t* plane = map + (size_t)(kc * 2) * ENC_PLANE_B + (size_t)(ENC_GUARD + pos) * 16;
+        *reinterpret_cast<uint4*>(plane) = hi4;
+        *reinterpret_cast<uint4*>(plane + ENC_PLANE_B) = lo4;
+      }
+    }
+  }
+}
+
+// ---- 3x3 convolution as implicit GEMM on tcgen05 -----------------------------------------------------------
+struct ConvParams {
+  const uint8_t* in_map;    // CIN channels
+  const uint8_t* w_image;   // [hi|lo][tap 9][chunk CIN/8][NPAD rows][8] bf16, then bias fp32[NPAD]
+  const uint8_t* res_map;   // residual input (same channel count as the output) or null
+  uint8_t* out_map;         // bf16 hi/lo planes of NPAD channels, or null
+  float* out_nchw;          // (n_images, cout, 32, 32) fp32, or null
+  int n_images, cout, relu;
+};
+
+template <int CIN, int NPAD>
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_conv3x3(const __grid_constant__ ConvParams P) {
+  constexpr int KC = CIN / 8;                     // 16-byte channel chunks
+  constexpr int PLANES = KC * 2;
+  constexpr int STAGE_B = PLANES * ENC_WIN_B;
+  constexpr int W_B = 2 * 9 * KC * NPAD * 16;
+  constexpr uint32_t IDESC = make_idesc(NPAD, 128);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* w_s = smem;                                         // W_B bytes + bias
+  float* bias_s = reinterpret_cast<float*>(smem + W_B);
+  uint8_t* stage0 = smem + ((W_B + NPAD * 4 + 127) & ~127);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + ENC_STAGES * STAGE_B);
+  uint64_t* full = bars;                      // TMA bytes landed            (producer -> issuer)
+  uint64_t* mma_done = bars + ENC_STAGES;     // accumulator complete        (issuer -> epilogue)
+  uint64_t* stage_free = bars + 2 * ENC_STAGES;  // MMAs have read the stage   (issuer -> producer)
+  uint64_t* tmem_free = bars + 3 * ENC_STAGES;   // epilogue has read D        (epilogue -> issuer)
+  uint64_t* wbar = bars + 4 * ENC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (tid == 0) {
+    for (int s = 0; s < ENC_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(mma_done + s, 1);
+      mbar_init(stage_free + s, 1);
+      mbar_init(tmem_free + s, 4);
+    }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(ENC_STAGES * 32)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long items = (long long)P.n_images * ENC_TILES;
+  const long long first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (elect_one_sync()) {
+      mbar_expect_tx(wbar, W_B + NPAD * 4);
+      for (uint32_t off = 0; off < (uint32_t)(W_B + NPAD * 4); off += 32768) {
+        const uint32_t n = (uint32_t)(W_B + NPAD * 4) - off < 32768 ? (uint32_t)(W_B + NPAD * 4) - off : 32768;
+        bulk_g2s(w_s + off, P.w_image + off, n, wbar);
+      }
+      long long i = 0;
+      for (long long w = first; w < items; w += step, ++i) {
+        const int s = (int)(i % ENC_STAGES);
+        const uint32_t par = (uint32_t)((i / ENC_STAGES) & 1);
+        mbar_wait(stage_free + s, par ^ 1u);
+        const long long image = w / ENC_TILES;
+        const int tile = (int)(w % ENC_TILES);
+        const uint8_t* src = P.in_map + (size_t)image * enc_map_bytes(CIN) + (size_t)(ENC_GUARD + tile * 128 - ENC_HALO) * 16;
+        mbar_expect_tx(full + s, STAGE_B);
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl)
+          bulk_g2s(stage0 + s * STAGE_B + pl * ENC_WIN_B, src + (size_t)pl * ENC_PLANE_B, ENC_WIN_B, full + s);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------------------------------- MMA issuer
+    mbar_wait(wbar, 0);
+    if (elect_one_sync()) {
+      const uint32_t w_addr = smem_u32(w_s);
+      long long i = 0;
+      for (long long w = first; w < items; w += step, ++i) {
+        const int s = (int)(i % ENC_STAGES);
+        const uint32_t par = (uint32_t)((i / ENC_STAGES) & 1);
+        mbar_wait(tmem_free + s, par ^ 1u);
+        mbar_wait(full + s, par);
+        tc_fence_after();
+        const uint32_t st_addr = smem_u32(stage0 + s * STAGE_B);
+        const uint32_t d = tmem_base + s * 32;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int shift = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1);
+#pragma unroll
+          for (int ks = 0; ks < CIN / 16; ++ks) {
+            // A: plane (chunk 2 ks, hi|lo) at the shifted position; the second K chunk is the next chunk's plane
+            const uint32_t a_hi = st_addr + (uint32_t)((2 * ks) * 2) * ENC_WIN_B + (uint32_t)shift * 16;
+            const uint32_t a_lo = a_hi + ENC_WIN_B;
+            const uint64_t da_hi = make_desc_interleave(a_hi, 2 * ENC_WIN_B, 128);
+            const uint64_t da_lo = make_desc_interleave(a_lo, 2 * ENC_WIN_B, 128);
+            // B: [hi|lo][tap][chunk][NPAD][8]
+            const uint32_t b_hi = w_addr + (uint32_t)((tap * KC + 2 * ks) * NPAD) * 16;
+            const uint32_t b_lo = b_hi + 9 * KC * NPAD * 16;
+            const uint64_t db_hi = make_desc_interleave(b_hi, NPAD * 16, 128);
+            const uint64_t db_lo = make_desc_interleave(b_lo, NPAD * 16, 128);
+            mma_ss(d, da_hi, db_hi, IDESC, acc);
+            acc = 1;
+            mma_ss(d, da_lo, db_hi, IDESC, 1);
+            mma_ss(d, da_hi, db_lo, IDESC, 1);
+          }
+        }
+        tc_commit(mma_done + s);
+        tc_commit(stage_free + s);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------------------------- epilogue groups
+    const int eg = (warp - 4) >> 2;                 // group 0 handles even items, group 1 odd items
+    const int quad = warp & 3;
+    const int r = quad * 32 + (tid & 31);           // row of the tile == TMEM lane
+    mbar_wait(wbar, 0);                             // bias is in shared memory
+    long long i = 0;
+    for (long long w = first; w < items; w += step, ++i) {
+      if ((int)(i & 1) != eg) continue;
+      const int s = (int)(i % ENC_STAGES);
+      const uint32_t par = (uint32_t)((i / ENC_STAGES) & 1);
+      const long long image = w / ENC_TILES;
+      const int pos = (int)(w % ENC_TILES) * 128 + r;
+      const bool valid = enc_valid(pos);
+      mbar_wait(mma_done + s, par);
+      tc_fence_after();
+      uint32_t d[NPAD];
+      const uint32_t taddr = tmem_base + s * 32 + ((uint32_t)(quad * 32) << 16);
+      tmem_ld16(taddr, reinterpret_cast<uint32_t(&)[16]>(d[0]));
+      if (NPAD == 32) tmem_ld16(taddr + 16, reinterpret_cast<uint32_t(&)[16]>(d[NPAD - 16]));
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(tmem_free + s);  // D[s] may be overwritten by the item after next
+
+      const size_t plane_off = (size_t)(ENC_GUARD + pos) * 16;
+#pragma unroll
+      for (int kc = 0; kc < NPAD / 8; ++kc) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(d[kc * 8 + j]) + bias_s[kc * 8 + j];
+        if (P.res_map != nullptr) {
+          const uint8_t* rp = P.res_map + (size_t)image * enc_map_bytes(NPAD) + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
+          float x[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(rp)), __ldg(reinterpret_cast<const uint4*>(rp + ENC_PLANE_B)), x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += x[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (P.relu) v[j] = fmaxf(v[j], 0.0f);
+          if (!valid) v[j] = 0.0f;
+        }
+        if (P.out_map != nullptr) {
+          uint4 hi4, lo4;
+          split8(v, hi4, lo4);
+          uint8_t* op = P.out_map + (size_t)image * enc_map_bytes(NPAD) + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
+          *reinterpret_cast<uint4*>(op) = hi4;
+          *reinterpret_cast<uint4*>(op + ENC_PLANE_B) = lo4;
+        }
+        if (P.out_nchw != nullptr && valid) {
+          const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (kc * 8 + j < P.cout) P.out_nchw[(((size_t)image * P.cout + kc * 8 + j) * 32 + y) * 32 + x] = v[j];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ENC_STAGES * 32) : "memory");
+  }
+}
+
+template <int CIN, int NPAD>
+static int launch_conv(const ConvParams& P, cudaStream_t stream) {
+  constexpr int W_B = 2 * 9 * (CIN / 8) * NPAD * 16;
+  constexpr int STAGE_B = (CIN / 8) * 2 * ENC_WIN_B;
+  const size_t smem = ((W_B + NPAD * 4 + 127) & ~127) + (size_t)ENC_STAGES * STAGE_B + 256;
+  static thread_local int configured_dev = -1;
+  static thread_local size_t window = 0;
+  int dev = 0, sms = 148;
+  MMF_CUDA(cudaGetDevice(&dev));
+  MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (configured_dev != dev) {
+    int rc = opt_in_shared_memory(k_enc_conv3x3<CIN, NPAD>, &window);
+    if (rc) return rc;
+    configured_dev = dev;
+  }
+  MMF_REQUIRE(smem <= window, "conv3x3 needs %zu B of shared memory (window %zu B)", smem, window);
+  long long grid = (long long)P.n_images * ENC_TILES;
+  if (grid > sms) grid = sms;
+  k_enc_conv3x3<CIN, NPAD><<<(unsigned)grid, ENC_THREADS, smem, stream>>>(P);
+  MMF_LAUNCH_CHECK("k_enc_conv3x3");
+  return MMF_OK;
+}
+
+size_t enc_map_bytes_host(int channels) { return enc_map_bytes(channels); }
+
+int launch_enc_stem(int n_images, const float* images, const float* w, void* out_map, cudaStream_t stream) {
+  if (n_images == 0) return MMF_OK;
+  int dev = 0, sms = 148;
+  MMF_CUDA(cudaGetDevice(&dev));
+  MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = n_images < (long long)sms * 4 ? n_images : (long long)sms * 4;
+  k_enc_stem<<<(unsigned)grid, 256, 0, stream>>>(images, w, static_cast<uint8_t*>(out_map), n_images);
+  MMF_LAUNCH_CHECK("k_enc_stem");
+  return MMF_OK;
+}
+
+int launch_enc_conv3x3(int n_images, int cin, int cout, const void* in_map, const void* w_image, const void* res_map,
+                       int relu, void* out_map, float* out_nchw, cudaStream_t stream) {
+  if (n_images == 0) return MMF_OK;
+  ConvParams P;
+  P.in_map = static_cast<const uint8_t*>(in_map);
+  P.w_image = static_cast<const uint8_t*>(w_image);
+  P.res_map = static_cast<const uint8_t*>(res_map);
+  P.out_map = static_cast<uint8_t*>(out_map);
+  P.out_nchw = out_nchw;
+  P.n_images = n_images;
+  P.cout = cout;
+  P.relu = relu;
+  const int npad = cout <= 16 ? 16 : 32;
+  if (cin == 32 && npad == 32) return launch_conv<32, 32>(P, stream);
+  if (cin == 32 && npad == 16) return launch_conv<32, 16>(P, stream);
+  if (cin == 16 && npad == 16) return launch_conv<16, 16>(P, stream);
+  set_error("conv3x3: unsupported channel counts %d -> %d (supported: 32->32, 32->16, 16->(<=16))", cin, cout);
+  return MMF_E_INVALID;
+}
+
+}  // namespace mmf

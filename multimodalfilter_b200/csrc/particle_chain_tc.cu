@@ -495,22 +495,6 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
 //     of the group's TMEM slice, so K step k of layer l+1 is issued as soon as chunk k of layer l's epilogue is
 //     done, while the group is still working on chunks k+1...: the group's serial chain per layer shrinks from
 //     "epilogue + 12 MMAs + commit latency" to "epilogue + 3 MMAs + commit latency".
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // publish chunk `chunk` of the A operand: stores retired -> ordered before the arrive the issuer observes
 __device__ __forceinline__ void publish_chunk(uint64_t* cbar, int chunk) {
   tc_wait_st();

@@ -1,0 +1,97 @@
+"""Image observation encoder with a fused sm_100a convolutional trunk.
+
+``ImageEncoder`` IS the reference's ``nn.Sequential`` (same children, same ``state_dict`` keys:
+ref: crossmodal/push_models/layers.py:93-104, crossmodal/door_models/layers.py:43-63); only its forward
+changes: under ``torch.no_grad()`` on a CUDA device the Conv2d layers run through ``mmf_enc_stem`` /
+``mmf_enc_conv3x3`` (tensor cores, bf16 hi/lo split operands, fp32 accumulation) and the Flatten/Linear tail
+stays with torch.  With autograd enabled (encoder training / pre-training) the plain module path runs, so
+gradients are untouched.  There is no CPU variant of the fused trunk: on a CPU tensor the module is the
+ordinary torch Sequential, exactly as in the reference.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .fannypack.nn import resblocks
+
+CHUNK_IMAGES = 4096  # images per pass of the trunk: bounds the activation-map workspace to ~2.2 GB
+
+
+def _is(m, cls, **attrs):
+    return isinstance(m, cls) and all(getattr(m, k) == v for k, v in attrs.items())
+
+
+class ImageEncoder(nn.Sequential):
+    fused_trunk = True  # set False (class or instance) to force the torch path
+
+    def _trunk(self):
+        """The Conv2d layers if this Sequential has the default (non-pooled) reference architecture, else None."""
+        m = list(self.children())
+        ok = (
+            len(m) >= 8
+            and _is(m[0], nn.Conv2d, in_channels=1, out_channels=32, kernel_size=(5, 5), padding=(2, 2))
+            and isinstance(m[1], nn.ReLU)
+            and isinstance(m[2], resblocks.Conv2d)
+            and _is(m[2].block1, nn.Conv2d, in_channels=32, out_channels=32, kernel_size=(3, 3), padding=(1, 1))
+            and _is(m[2].block2, nn.Conv2d, in_channels=32, out_channels=32, kernel_size=(3, 3), padding=(1, 1))
+            and _is(m[3], nn.Conv2d, in_channels=32, out_channels=16, kernel_size=(3, 3), padding=(1, 1))
+            and isinstance(m[4], nn.ReLU)
+            and _is(m[5], nn.Conv2d, in_channels=16, kernel_size=(3, 3), padding=(1, 1))
+            and m[5].out_channels <= 16
+            and isinstance(m[6], nn.Flatten)
+        )
+        if not ok:
+            return None
+        convs = [m[0], m[2].block1, m[2].block2, m[3], m[5]]
+        if any(c.stride != (1, 1) or c.dilation != (1, 1) or c.groups != 1 or c.bias is None for c in convs):
+            return None
+        return convs
+
+    def _packed(self, convs, device):
+        key = tuple((p.data_ptr(), p._version) for c in convs for p in (c.weight, c.bias)) + (str(device),)
+        cache = self.__dict__.get("_mmf_packed")
+        if cache is None or cache[0] != key:
+            packed = [ops.enc_pack_stem(convs[0])] + [ops.enc_pack_conv3x3(c) for c in convs[1:]]
+            cache = (key, packed)
+            self.__dict__["_mmf_packed"] = cache
+        return cache[1]
+
+    def _workspace(self, device):
+        ws = self.__dict__.get("_mmf_ws")
+        if ws is None or ws[0] != str(device):
+            maps = [ops.enc_new_map(CHUNK_IMAGES, 32, device) for _ in range(3)]
+            ws = (str(device), maps)
+            self.__dict__["_mmf_ws"] = ws
+        return ws[1]
+
+    def forward(self, x):
+        convs = self._trunk() if self.fused_trunk else None
+        use_fused = (
+            convs is not None
+            and x.is_cuda
+            and x.dtype == torch.float32
+            and x.dim() == 4
+            and tuple(x.shape[1:]) == (1, 32, 32)
+            and not torch.is_grad_enabled()
+        )
+        if not use_fused:
+            return super().forward(x)
+        w_stem, w2a, w2b, w3, w4 = self._packed(convs, x.device)
+        map_x, map_t, map_y = self._workspace(x.device)
+        cout = convs[4].out_channels
+        tail = list(self.children())[6:]
+        outs = []
+        images = x.reshape(-1, 32, 32).contiguous()
+        for lo in range(0, images.shape[0], CHUNK_IMAGES):
+            chunk = images[lo:lo + CHUNK_IMAGES]
+            n = chunk.shape[0]
+            ops.enc_stem(chunk, w_stem, map_x)                                                # Conv 5x5 + ReLU
+            ops.enc_conv3x3(n, 32, 32, map_x, w2a, relu=True, out_map=map_t)                   # resblock.block1 + ReLU
+            ops.enc_conv3x3(n, 32, 32, map_t, w2b, res_map=map_x, relu=True, out_map=map_y)    # block2 + x, ReLU
+            ops.enc_conv3x3(n, 32, 16, map_y, w3, relu=True, out_map=map_x)                    # Conv 32->16 + ReLU (reuses map_x)
+            h = torch.empty((n, cout, 32, 32), device=x.device, dtype=torch.float32)
+            ops.enc_conv3x3(n, 16, cout, map_x, w4, relu=False, out_nchw=h)                    # Conv 16->8
+            for layer in tail:
+                h = layer(h)
+            outs.append(h)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

@@ -148,6 +148,55 @@ def pf_heads_weight_grads(act, delta):
     return dW
 
 
+# ---- image encoder trunk ------------------------------------------------------------------------------------
+def enc_map_bytes(channels: int) -> int:
+    return int(_lib.load().mmf_enc_map_bytes(channels))
+
+
+def enc_new_map(n_images: int, channels: int, device) -> torch.Tensor:
+    """Zero-initialised activation map (bf16 hi/lo planes); the zero guards are never written by the kernels."""
+    return torch.zeros(n_images * enc_map_bytes(channels), dtype=torch.uint8, device=device)
+
+
+def enc_pack_stem(conv) -> torch.Tensor:
+    """Conv2d(1, 32, 5) -> fp32 [tap 25][32] + bias[32]."""
+    w = conv.weight.detach().float().reshape(32, 25).t().contiguous().reshape(-1)
+    return torch.cat([w, conv.bias.detach().float()]).contiguous()
+
+
+def enc_pack_conv3x3(conv) -> torch.Tensor:
+    """Conv2d(cin, cout, 3) -> bf16 [hi|lo][tap][cin/8][npad][8] + fp32 bias[npad] as one byte tensor."""
+    w = conv.weight.detach().float()
+    cout, cin = w.shape[0], w.shape[1]
+    npad = 32 if cout > 16 else 16
+    wp = torch.zeros(npad, cin, 3, 3, device=w.device)
+    wp[:cout] = w
+    hi = wp.to(torch.bfloat16)
+    lo = (wp - hi.float()).to(torch.bfloat16)
+
+    def layout(t):  # (npad, cin, 3, 3) -> (tap, cin/8, npad, 8)
+        return t.permute(2, 3, 1, 0).reshape(9, cin // 8, 8, npad).permute(0, 1, 3, 2).contiguous()
+
+    img = torch.stack([layout(hi), layout(lo)]).contiguous().view(torch.uint8).reshape(-1)
+    bias = torch.zeros(npad, device=w.device)
+    bias[:cout] = conv.bias.detach().float()
+    return torch.cat([img, bias.view(torch.uint8).reshape(-1)]).contiguous()
+
+
+def enc_stem(images, w_stem, out_map):
+    lib = _lib.load()
+    n = images.shape[0]
+    _lib.check(PROFILE.run("enc_stem", 1, lib.mmf_enc_stem, n, _lib.ptr(images), _lib.ptr(w_stem), _lib.ptr(out_map),
+                           _lib.stream_of(images)))
+
+
+def enc_conv3x3(n_images, cin, cout, in_map, w_image, *, res_map=None, relu=True, out_map=None, out_nchw=None):
+    lib = _lib.load()
+    _lib.check(PROFILE.run("enc_conv3x3", 1, lib.mmf_enc_conv3x3, n_images, cin, cout, _lib.ptr(in_map),
+                           _lib.ptr(w_image), _lib.ptr(res_map), int(relu), _lib.ptr(out_map), _lib.ptr(out_nchw),
+                           _lib.stream_of(in_map)))
+
+
 def pf_init(mean, covariance, eps_MNsd):
     """R2: (N,sd), (N,sd,sd), (M,N,sd) -> particle_states (N,M,sd), particle_log_weights (N,M)."""
     lib = _lib.load()

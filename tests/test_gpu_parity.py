@@ -542,3 +542,73 @@ def test_heads_backward_kernel_matches_autograd():
             for l in range(L):
                 assert_close(delta[k, l].cpu(), zs[1 + l].grad.cpu(), 2e-4, msg=f"{name} head {k} delta {l}")
             assert_close(delta[k, L].cpu(), zs[0].grad.cpu(), 2e-4, msg=f"{name} head {k} input-layer delta")
+
+
+# ---- image encoder trunk: tcgen05 implicit-GEMM convolutions vs torch fp32 ---------------
+def _unmap(m, n, ch):
+    """bf16 hi/lo planes -> (n, ch, 32, 32) fp32"""
+    t = m.view(n, ops.enc_map_bytes(ch)).view(torch.bfloat16).reshape(n, ch // 8, 2, 1280, 8).float()
+    v = (t[:, :, 0] + t[:, :, 1])[:, :, 64:64 + 1088].reshape(n, ch // 8, 32, 34, 8)[:, :, :, :32]
+    return v.permute(0, 1, 4, 2, 3).reshape(n, ch, 32, 32)
+
+
+@pytest.mark.parametrize("n", [1, 37, 300])
+def test_encoder_conv_layers_match_torch(n):
+    import torch.nn.functional as F
+    torch.manual_seed(n)
+    img = (torch.rand(n, 32, 32, device=DEV) * 2 - 1).contiguous()
+    img[0, :3] = 0.0
+    c1 = torch.nn.Conv2d(1, 32, 5, padding=2).to(DEV)
+    c2a, c2b = torch.nn.Conv2d(32, 32, 3, padding=1).to(DEV), torch.nn.Conv2d(32, 32, 3, padding=1).to(DEV)
+    c3, c4 = torch.nn.Conv2d(32, 16, 3, padding=1).to(DEV), torch.nn.Conv2d(16, 8, 3, padding=1).to(DEV)
+    tol = 5e-5  # activations are kept as bf16 hi + lo (2^-18 relative); accumulation is fp32
+    with torch.no_grad():
+        x_ref = F.relu(c1(img[:, None]))
+        mx, mt, my = (ops.enc_new_map(n, 32, DEV) for _ in range(3))
+        mz = ops.enc_new_map(n, 16, DEV)
+        ops.enc_stem(img, ops.enc_pack_stem(c1), mx)
+        assert_close(_unmap(mx, n, 32).cpu(), x_ref.cpu(), tol, msg="5x5 stem")
+        ops.enc_conv3x3(n, 32, 32, mx, ops.enc_pack_conv3x3(c2a), relu=True, out_map=mt)
+        t_ref = F.relu(c2a(x_ref))
+        assert_close(_unmap(mt, n, 32).cpu(), t_ref.cpu(), tol, msg="conv 32->32")
+        ops.enc_conv3x3(n, 32, 32, mt, ops.enc_pack_conv3x3(c2b), res_map=mx, relu=True, out_map=my)
+        y_ref = F.relu(c2b(t_ref) + x_ref)
+        assert_close(_unmap(my, n, 32).cpu(), y_ref.cpu(), tol, msg="conv 32->32 + residual")
+        ops.enc_conv3x3(n, 32, 16, my, ops.enc_pack_conv3x3(c3), relu=True, out_map=mz)
+        z_ref = F.relu(c3(y_ref))
+        assert_close(_unmap(mz, n, 16).cpu(), z_ref.cpu(), tol, msg="conv 32->16")
+        out = torch.empty(n, 8, 32, 32, device=DEV)
+        ops.enc_conv3x3(n, 16, 8, mz, ops.enc_pack_conv3x3(c4), relu=False, out_nchw=out)
+        assert_close(out.cpu(), c4(z_ref).cpu(), tol, msg="conv 16->8 (NCHW output)")
+        # the zero guards and the pad columns of every map are still zero (the next layer's padding depends on it)
+        for m, ch in ((mx, 32), (mt, 32), (my, 32), (mz, 16)):
+            t = m.view(n, ch // 8, 2, 1280, 16)
+            assert int(t[:, :, :, :64].count_nonzero()) == 0 and int(t[:, :, :, 64 + 1088:].count_nonzero()) == 0
+            pads = t[:, :, :, 64:64 + 1088].reshape(n, ch // 8, 2, 32, 34, 16)[:, :, :, :, 32:]
+            assert int(pads.count_nonzero()) == 0
+
+
+@pytest.mark.parametrize("batch", [3, 4096 + 5])
+def test_image_encoder_module_fused_trunk_matches_torch_path(batch):
+    from multimodalfilter_b200.encoders import ImageEncoder
+    filt = fill_parameters(M.PushCrossmodalParticleFilter(), seed=3).to(DEV).eval()
+    enc = filt.measurement_model.measurement_models[0].observation_image_layers
+    assert isinstance(enc, ImageEncoder) and enc._trunk() is not None
+    g = torch.Generator(device=DEV).manual_seed(batch)
+    x = torch.rand(batch, 1, 32, 32, device=DEV, generator=g) * 2 - 1
+    x[1] = 0.0  # a blacked-out image
+    with torch.no_grad():
+        ops.PROFILE.reset(enabled=True)
+        fused_out = enc(x)
+        launched = ops.PROFILE.collect()["launches"]
+        ops.PROFILE.reset(enabled=False)
+        enc.fused_trunk = False
+        try:
+            torch_out = enc(x)
+        finally:
+            del enc.fused_trunk
+    assert launched >= 5, "the fused trunk did not run"
+    assert_close(fused_out.cpu(), torch_out.cpu(), 5e-5, msg="encoder features")
+    # with autograd on the module is the plain torch Sequential (training path untouched)
+    y = enc(x[:2])
+    assert y.requires_grad

@@ -40,3 +40,15 @@ for fmt in ("default", "channels_last"):
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         enc(x); torch.cuda.synchronize(); a = ev(); enc(x); b = ev(); torch.cuda.synchronize()
     print(f"image encoder, 16384 images, {fmt}, bf16 autocast: {a.elapsed_time(b):.2f} ms")
+torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.benchmark = True
+for fmt in ("default", "channels_last"):
+    enc = plan.heads[0].head.observation_image_layers
+    x = o["image"].reshape(T * N, 1, 32, 32)[:16384]
+    if fmt == "channels_last":
+        enc = enc.to(memory_format=torch.channels_last); x = x.contiguous(memory_format=torch.channels_last)
+    else:
+        enc = enc.to(memory_format=torch.contiguous_format)
+    with torch.no_grad():
+        ref = enc(x); enc(x); torch.cuda.synchronize(); a = ev(); y = enc(x); b = ev(); torch.cuda.synchronize()
+    print(f"cudnn.benchmark=True fp32 {fmt}: {a.elapsed_time(b):.2f} ms per 16384 images ({a.elapsed_time(b)*25:.0f} ms for 409600)")
