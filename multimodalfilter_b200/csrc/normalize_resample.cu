@@ -87,46 +87,164 @@ __device__ __forceinline__ int lower_bound_cdf(const float* cdf, int M, float to
   return lo < M - 1 ? lo : M - 1;
 }
 
-// per-trajectory scratch arrays, in floats: [cdf Mpad | segoff Mpad/8 | gtot Mpad/256 + 4 | diff Mpad]
+// NB independent draws searched in lock step: every probe step issues NB independent shared-memory loads, so the
+// dependent load -> compare -> load chain of one binary search overlaps with the others (per-lane memory-level
+// parallelism; the single-draw form left the kernel latency-bound).  Same decisions as lower_bound_cdf.
+constexpr int NB = 4;
+__device__ __forceinline__ void lower_bound_batch(const float* cdf, int M, float total, const double (&u)[NB],
+                                                  int (&idx)[NB], int iters) {
+  float c0[NB], band[NB];
+  int lo[NB], hi[NB];
+  bool near[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    c0[b] = (float)(u[b] * (double)total);
+    band[b] = fmaxf(c0[b] * 4.8e-7f, 1e-37f);
+    lo[b] = 0;
+    hi[b] = M;
+    near[b] = !(u[b] > 0.0);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const bool open = lo[b] < hi[b];
+      const int mid = open ? lo[b] + ((hi[b] - lo[b]) >> 1) : 0;
+      const float c = cdf[mid];
+      near[b] |= open && fabsf(c - c0[b]) <= band[b];
+      if (open) {
+        if (c < c0[b]) lo[b] = mid + 1; else hi[b] = mid;
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    if (near[b]) {  // rare: an entry within a few ulp of the threshold was probed -> exact predicate
+      const float cstar = cdf_threshold(total, u[b]);
+      int l = 0, h = M;
+      while (l < h) {
+        const int mid = l + ((h - l) >> 1);
+        if (cdf[mid] < cstar) l = mid + 1; else h = mid;
+      }
+      lo[b] = l;
+    }
+    idx[b] = lo[b] < M - 1 ? lo[b] : M - 1;
+  }
+}
+
+// Guide-table (bucket) inverse CDF for the warp-per-trajectory path.  f(c) = min(int(c * scale), K) is monotone
+// in c, and guide[b] = number of CDF entries with f < b; hence for a draw with threshold c0 and b = f(c0) the
+// lower bound lies in [guide[b], guide[b + 1]]: a bucket is hit with probability 1/K whatever it holds, so the
+// expected range is M / K ~ 1 entry, against log2(M) dependent probes of a binary search.  Decisions are those
+// of lower_bound_cdf: the final neighbours decide whether the exact threshold c* has to be consulted.
+__device__ __forceinline__ int guided_lower_bound(const float* cdf, const uint16_t* guide, int M, int K, float scale,
+                                                  float total, double u) {
+  // the search key only has to be within a few ulp of the exact threshold (the band check below sends close
+  // calls to the exact predicate), so it is formed in fp32: no fp64 arithmetic on the per-draw path
+  const float uf = (float)u;
+  const float c0 = uf * total;
+  int b = (int)(c0 * scale);
+  b = b < 0 ? 0 : (b > K ? K : b);
+  int lo = guide[b], hi = guide[b + 1];
+  while (hi - lo > 4) {  // crowded bucket: bisect down to a short run first
+    const int mid = lo + ((hi - lo) >> 1);
+    if (cdf[mid] < c0) lo = mid + 1; else hi = mid;
+  }
+  while (lo < hi && cdf[lo] < c0) ++lo;
+  const float band = fmaxf(c0 * 9.6e-7f, 1e-37f);  // >= 8 ulp: fp32 key (<= 2 ulp off) + distance key..c* (<= 2 ulp)
+  bool near = !(uf > 0.0f);
+  if (lo < M) near |= fabsf(cdf[lo] - c0) <= band;
+  if (lo > 0) near |= fabsf(cdf[lo - 1] - c0) <= band;
+  if (near) {
+    const float cstar = cdf_threshold(total, u);
+    lo = 0;
+    hi = M;
+    while (lo < hi) {
+      const int mid = lo + ((hi - lo) >> 1);
+      if (cdf[mid] < cstar) lo = mid + 1; else hi = mid;
+    }
+  }
+  return lo < M - 1 ? lo : M - 1;
+}
+
+// per-trajectory scratch arrays, in floats: [cdf Mpad | segoff Mpad/8 | gtot Mpad/256 + 4 | diff Mpad | guide (u16) Mpad + 2]
 __host__ __device__ inline size_t trajectory_scratch_floats(int M, bool soft) {
   const size_t Mpad = ((size_t)(M + GROUP - 1) / GROUP) * GROUP;
-  const size_t n = Mpad + Mpad / SEG + Mpad / GROUP + 4 + (soft ? Mpad : 0);
+  const size_t guide = Mpad <= 65536 ? (Mpad + 2 + 1) / 2 : 0;  // u16 guide table of the warp-per-trajectory search
+  const size_t n = Mpad + Mpad / SEG + Mpad / GROUP + 4 + (soft ? Mpad : 0) + guide;
   return (n + 63) & ~(size_t)63;  // slices stay 256-byte aligned (vector loads in the serial scan)
 }
 
+// COOP = threads that cooperate on one trajectory:
+//   COOP = NR_TPB: one CTA per trajectory (any M; block-wide reductions through shared memory);
+//   COOP = 32    : one WARP per trajectory (M <= NR_WARP_MAX_M): eight independent trajectories per CTA, warp
+//                  shuffles instead of block barriers, so the serial CDF chain of one trajectory (one lane, a
+//                  dependent fp32 add every ~4 cycles) hides behind the streaming phases of the 40+ other warps
+//                  resident on the SM.  This is the path of BASELINE configs C1/C3/C4 (M = 30 ... 1000).
 // GLOBAL_WS = false: the trajectory's arrays live in shared memory (M up to ~48 k);
 // GLOBAL_WS = true : they live in a caller-provided global workspace, one slice per CTA (any M: the
 //                    1 k ... 1 M particle sweep of BASELINE config C5 runs through this instantiation).
-template <bool GLOBAL_WS>
-__global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_constant__ ResampleParams P, float* workspace) {
+template <int COOP>
+__device__ __forceinline__ void coop_sync() {
+  if (COOP == 32) __syncwarp(); else __syncthreads();
+}
+template <int COOP>
+__device__ __forceinline__ float coop_max(float v, float* scratch) {
+  return COOP == 32 ? warp_max(v) : block_max(v, scratch);
+}
+template <int COOP>
+__device__ __forceinline__ float coop_sum(float v, float* scratch) {
+  return COOP == 32 ? warp_sum(v) : block_sum(v, scratch);
+}
+
+constexpr int NR_WARP_TPB = 128;      // warp-per-trajectory CTAs: 4 trajectories each
+constexpr int NR_WARP_CTAS_PER_SM = 7;  // 28 resident warps per SM: C3's 4096 trajectories are ONE wave on 148 SMs
+
+template <bool GLOBAL_WS, int COOP>
+__global__ void __launch_bounds__(COOP == 32 ? NR_WARP_TPB : NR_TPB, COOP == 32 ? NR_WARP_CTAS_PER_SM : 1) k_normalize_resample(const __grid_constant__ ResampleParams P, float* workspace) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float scratch[32];
+  __shared__ int cand_w[NR_TPB / 32];
+  constexpr int UNITS_PER_CTA = (COOP == 32 ? NR_WARP_TPB : NR_TPB) / COOP;
   const int M = P.M, sd = P.sd, tid = threadIdx.x;
+  const int cid = tid % COOP;                       // index inside the cooperating set
+  const int unit = blockIdx.x * UNITS_PER_CTA + tid / COOP;
+  const int units = gridDim.x * UNITS_PER_CTA;
   const int Mpad = ((M + GROUP - 1) / GROUP) * GROUP;
   const bool soft = P.alpha < 1.0f;
-  float* cdf = GLOBAL_WS ? workspace + (size_t)blockIdx.x * trajectory_scratch_floats(M, soft) : sm;  // log-weights first, CDF later
+  const size_t slice = trajectory_scratch_floats(M, soft);
+  float* cdf = GLOBAL_WS ? workspace + (size_t)blockIdx.x * slice : sm + (size_t)(tid / COOP) * slice;  // log-weights first, CDF later
   float* segoff = cdf + Mpad;     // Mpad / SEG
   float* gtot = segoff + Mpad / SEG;  // Mpad / GROUP (+4)
   float* diff = gtot + Mpad / GROUP + 4;  // Mpad (only when alpha < 1): logw - logits
+  uint16_t* guide = reinterpret_cast<uint16_t*>(diff + (soft ? Mpad : 0));  // Mpad + 2 entries (warp path only)
   const bool resample = P.mode != MMF_RESAMPLE_NONE;
 
-  for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
-    __syncthreads();
+  for (int n = unit; n < P.N; n += units) {
+    coop_sync<COOP>();
     float lmax;
     if (P.logits_in == nullptr) {
       // ---- normalise: logw = l - logsumexp(l) ----------------------------------------------------
       const float* lw = P.logw_unnorm + (size_t)n * M;
       float mx = -INFINITY;
-      for (int i = tid; i < M; i += NR_TPB) {
-        const float l = lw[i];
-        cdf[i] = l;
-        mx = fmaxf(mx, l);
+      for (int base = 0; base < M; base += COOP * NB) {  // NB independent global loads in flight per thread
+        float l[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int i = base + b * COOP + cid;
+          l[b] = i < M ? lw[i] : -INFINITY;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int i = base + b * COOP + cid;
+          if (i < M) cdf[i] = l[b];
+          mx = fmaxf(mx, l[b]);
+        }
       }
-      mx = block_max(mx, scratch);
+      mx = coop_max<COOP>(mx, scratch);
       const float shift = (mx == -INFINITY || mx == INFINITY) ? 0.0f : mx;
       float s = 0.0f;
-      for (int i = tid; i < M; i += NR_TPB) s += expf(cdf[i] - shift);
-      s = block_sum(s, scratch);
+      for (int i = cid; i < M; i += COOP) s += expf(cdf[i] - shift);
+      s = coop_sum<COOP>(s, scratch);
       const float lse = shift + logf(s);
 
       // ---- estimate ------------------------------------------------------------------------------
@@ -134,42 +252,60 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
       float acc[MMF_MAX_SD] = {0.f, 0.f, 0.f, 0.f};
       float best = -INFINITY;
       int best_i = 0x7fffffff;
-      for (int i = tid; i < M; i += NR_TPB) {
-        const float l = cdf[i] - lse;
-        cdf[i] = l;
-        if (P.logw_norm_out) P.logw_norm_out[(size_t)n * M + i] = l;
-        if (!resample) P.logw_out[(size_t)n * M + i] = l;
-        if (P.estimation == MMF_ESTIMATE_WEIGHTED_AVERAGE) {
-          const float wgt = expf(l);
+      const bool weighted = P.estimation == MMF_ESTIMATE_WEIGHTED_AVERAGE;
+      for (int base = 0; base < M; base += COOP * NB) {
+        float xv[NB][MMF_MAX_SD];
+        if (weighted) {
 #pragma unroll
-          for (int d = 0; d < MMF_MAX_SD; ++d)
-            if (d < sd) acc[d] = fmaf(wgt, xs[(size_t)i * sd + d], acc[d]);
-        } else if (l > best) {
-          best = l;
-          best_i = i;
+          for (int b = 0; b < NB; ++b) {
+            const int i = base + b * COOP + cid;
+#pragma unroll
+            for (int d = 0; d < MMF_MAX_SD; ++d) xv[b][d] = (d < sd && i < M) ? xs[(size_t)i * sd + d] : 0.0f;
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int i = base + b * COOP + cid;
+          if (i < M) {
+            const float l = cdf[i] - lse;
+            cdf[i] = l;
+            if (P.logw_norm_out) P.logw_norm_out[(size_t)n * M + i] = l;
+            if (!resample) P.logw_out[(size_t)n * M + i] = l;
+            if (weighted) {
+              const float wgt = expf(l);
+#pragma unroll
+              for (int d = 0; d < MMF_MAX_SD; ++d)
+                if (d < sd) acc[d] = fmaf(wgt, xv[b][d], acc[d]);
+            } else if (l > best) {
+              best = l;
+              best_i = i;
+            }
+          }
         }
       }
       if (P.estimation == MMF_ESTIMATE_WEIGHTED_AVERAGE) {
 #pragma unroll
         for (int d = 0; d < MMF_MAX_SD; ++d) {
           if (d < sd) {
-            const float v = block_sum(acc[d], scratch);
-            if (tid == 0) P.est_out[(size_t)n * sd + d] = v;
+            const float v = coop_sum<COOP>(acc[d], scratch);
+            if (cid == 0) P.est_out[(size_t)n * sd + d] = v;
           }
         }
       } else {
-        const float gbest = block_max(best, scratch);
+        const float gbest = coop_max<COOP>(best, scratch);
         int cand = (best == gbest) ? best_i : 0x7fffffff;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
-        __shared__ int cand_w[NR_TPB / 32];
-        __syncthreads();
-        if ((tid & 31) == 0) cand_w[tid >> 5] = cand;
-        __syncthreads();
-        int win = cand_w[0];
-        for (int w = 1; w < NR_TPB / 32; ++w) win = min(win, cand_w[w]);
+        int win = cand;
+        if (COOP != 32) {
+          __syncthreads();
+          if ((tid & 31) == 0) cand_w[tid >> 5] = cand;
+          __syncthreads();
+          win = cand_w[0];
+          for (int w = 1; w < NR_TPB / 32; ++w) win = min(win, cand_w[w]);
+        }
         if (win == 0x7fffffff) win = 0;
-        if (tid < sd) P.est_out[(size_t)n * sd + tid] = xs[(size_t)win * sd + tid];
+        if (cid < sd) P.est_out[(size_t)n * sd + cid] = xs[(size_t)win * sd + cid];
       }
       if (!resample) continue;
 
@@ -177,7 +313,7 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
       float lm = -INFINITY;
       if (soft) {
         const float la = logf(P.alpha), lb = -logf((float)M) + logf(1.0f - P.alpha);
-        for (int i = tid; i < M; i += NR_TPB) {
+        for (int i = cid; i < M; i += COOP) {
           const float a = cdf[i] + la;
           const float m2 = fmaxf(a, lb);
           const float lg = m2 + logf(expf(a - m2) + expf(lb - m2));
@@ -186,25 +322,25 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
           lm = fmaxf(lm, lg);
         }
       } else {
-        for (int i = tid; i < M; i += NR_TPB) lm = fmaxf(lm, cdf[i]);
+        for (int i = cid; i < M; i += COOP) lm = fmaxf(lm, cdf[i]);
       }
-      lmax = block_max(lm, scratch);
+      lmax = coop_max<COOP>(lm, scratch);
     } else {
       const float* lg = P.logits_in + (size_t)n * M;
       float lm = -INFINITY;
-      for (int i = tid; i < M; i += NR_TPB) {
+      for (int i = cid; i < M; i += COOP) {
         const float l = lg[i];
         cdf[i] = l;
         lm = fmaxf(lm, l);
       }
-      lmax = block_max(lm, scratch);
+      lmax = coop_max<COOP>(lm, scratch);
     }
     if (P.logits_out)
-      for (int i = tid; i < M; i += NR_TPB) P.logits_out[(size_t)n * M + i] = cdf[i];
+      for (int i = cid; i < M; i += COOP) P.logits_out[(size_t)n * M + i] = cdf[i];
 
     // ---- pinned softmax numerators ------------------------------------------------------------------
-    for (int i = tid; i < Mpad; i += NR_TPB) cdf[i] = (i < M) ? exp_pinned(cdf[i] - lmax) : 0.0f;
-    __syncthreads();
+    for (int i = cid; i < Mpad; i += COOP) cdf[i] = (i < M) ? exp_pinned(cdf[i] - lmax) : 0.0f;
+    coop_sync<COOP>();
 
     // ---- CDF --------------------------------------------------------------------------------------------
     const bool strict = (P.mode == MMF_RESAMPLE_MULTINOMIAL_STRICT || P.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT);
@@ -212,11 +348,11 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
       // The chain of M dependent fp32 adds IS the definition (torch.multinomial's CPU order), so it cannot be
       // parallelised; what can be done is keep everything but the adds off the critical path: 16 values are
       // fetched per iteration with vector loads (independent of the running sum) and written back vectorised,
-      // leaving 4 cycles per element.  Other CTAs on the SM overlap their streaming phases with it.
-      if (tid == 0) {
+      // leaving 4 cycles per element.  Other warps / CTAs on the SM overlap their streaming phases with it.
+      if (cid == 0) {
         float run = 0.0f;
         float4* c4 = reinterpret_cast<float4*>(cdf);
-        const int blocks16 = Mpad / 16;  // padded entries are zero: adding them is exact and harmless
+        const int blocks16 = (M + 15) / 16;  // padded entries are zero: adding them is exact and harmless
         for (int b = 0; b < blocks16; ++b) {
           float4 v[4];
 #pragma unroll
@@ -232,11 +368,11 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
           for (int q = 0; q < 4; ++q) c4[b * 4 + q] = v[q];
         }
       }
-      __syncthreads();
+      coop_sync<COOP>();
     } else {
-      const int lane = tid & 31, wid = tid >> 5;
+      const int lane = tid & 31, wid = (tid % COOP) >> 5;
       const int groups = Mpad / GROUP;
-      for (int g = wid; g < groups; g += NR_TPB / 32) {
+      for (int g = wid; g < groups; g += COOP / 32) {
         const int s = g * 32 + lane;
         float* e = cdf + (size_t)s * SEG;
         float run = 0.0f;
@@ -255,8 +391,8 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
         segoff[s] = (lane == 0) ? 0.0f : excl;
         if (lane == 31) gtot[g] = t;
       }
-      __syncthreads();
-      if (tid == 0) {
+      coop_sync<COOP>();
+      if (cid == 0) {
         float run = 0.0f;
         for (int g = 0; g < groups; ++g) {
           const float t = gtot[g];
@@ -264,35 +400,80 @@ __global__ void __launch_bounds__(NR_TPB) k_normalize_resample(const __grid_cons
           run = __fadd_rn(run, t);
         }
       }
-      __syncthreads();
-      for (int i = tid; i < M; i += NR_TPB) {
+      coop_sync<COOP>();
+      for (int i = cid; i < M; i += COOP) {
         const float base = __fadd_rn(gtot[i / GROUP], segoff[i / SEG]);
         cdf[i] = __fadd_rn(base, cdf[i]);
       }
-      __syncthreads();
+      coop_sync<COOP>();
     }
     const float total = cdf[M - 1];
+    const int K = ((M + 31) / 32) * 32;  // guide buckets (<= Mpad)
+    const float scale = (float)K / total;
+    if (COOP == 32) {
+      for (int i = cid; i < M; i += 32) {
+        int fi = (int)(cdf[i] * scale);
+        fi = fi < 0 ? 0 : (fi > K ? K : fi);
+        int fp = -1;
+        if (i > 0) {
+          fp = (int)(cdf[i - 1] * scale);
+          fp = fp < 0 ? 0 : (fp > K ? K : fp);
+        }
+        for (int b = fp + 1; b <= fi; ++b) guide[b] = (uint16_t)i;
+      }
+      int fl = (int)(total * scale);
+      fl = fl < 0 ? 0 : (fl > K ? K : fl);
+      for (int b = fl + 1 + cid; b <= K + 1; b += 32) guide[b] = (uint16_t)M;
+      __syncwarp();
+    }
 
     // ---- inverse CDF + gather -----------------------------------------------------------------------
     const bool systematic = (P.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT || P.mode == MMF_RESAMPLE_SYSTEMATIC_FAST);
     const float uniform_lw = -logf((float)M);
     const double u0 = systematic ? P.uniforms[n] : 0.0;
-    for (int j = tid; j < P.M_out; j += NR_TPB) {
-      const double u = systematic ? (u0 + (double)j) / (double)P.M_out
-                                  : P.uniforms[(size_t)n * P.M_out + j];
-      const int idx = lower_bound_cdf(cdf, M, total, u);
-      if (P.idx_out) P.idx_out[(size_t)n * P.M_out + j] = idx;
-      if (P.states_out) {
-        const float* src = P.states + ((size_t)n * M + idx) * sd;
-        float* dst = P.states_out + ((size_t)n * P.M_out + j) * sd;
+    const int iters = 32 - __clz(M);  // probe steps until every [lo, hi) interval is empty
+    for (int base = 0; base < P.M_out; base += COOP * NB) {
+      double u[NB];
 #pragma unroll
-        for (int d = 0; d < MMF_MAX_SD; ++d)
-          if (d < sd) dst[d] = src[d];
+      for (int b = 0; b < NB; ++b) {
+        const int j = base + b * COOP + cid;
+        u[b] = j >= P.M_out ? 0.5 : systematic ? (u0 + (double)j) / (double)P.M_out : P.uniforms[(size_t)n * P.M_out + j];
       }
-      if (P.logw_out) P.logw_out[(size_t)n * P.M_out + j] = soft ? diff[idx] : uniform_lw;
+      int idx[NB];
+      if (COOP == 32) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) idx[b] = guided_lower_bound(cdf, guide, M, K, scale, total, u[b]);
+      } else {
+        lower_bound_batch(cdf, M, total, u, idx, iters);
+      }
+      float sv[NB][MMF_MAX_SD];
+      if (P.states_out) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float* src = P.states + ((size_t)n * M + idx[b]) * sd;
+#pragma unroll
+          for (int d = 0; d < MMF_MAX_SD; ++d) sv[b][d] = d < sd ? src[d] : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const int j = base + b * COOP + cid;
+        if (j < P.M_out) {
+          if (P.idx_out) P.idx_out[(size_t)n * P.M_out + j] = idx[b];
+          if (P.states_out) {
+            float* dst = P.states_out + ((size_t)n * P.M_out + j) * sd;
+#pragma unroll
+            for (int d = 0; d < MMF_MAX_SD; ++d)
+              if (d < sd) dst[d] = sv[b][d];
+          }
+          if (P.logw_out) P.logw_out[(size_t)n * P.M_out + j] = soft ? diff[idx[b]] : uniform_lw;
+        }
+      }
     }
   }
 }
+
+constexpr int NR_WARP_MAX_M = 2048;  // warp-per-trajectory path: 8 slices of <= ~20 KB per CTA
 
 static size_t resample_smem_bytes(int M, bool soft) { return trajectory_scratch_floats(M, soft) * sizeof(float); }
 
@@ -302,7 +483,10 @@ static int resample_window(size_t* window_out) {
   int dev = 0;
   MMF_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    int rc = opt_in_shared_memory(k_normalize_resample<false>, &window);
+    int rc = opt_in_shared_memory(k_normalize_resample<false, NR_TPB>, &window);
+    if (rc) return rc;
+    size_t w2 = 0;
+    rc = opt_in_shared_memory(k_normalize_resample<false, 32>, &w2);
     if (rc) return rc;
     configured_dev = dev;
   }
@@ -341,8 +525,22 @@ int launch_normalize_resample(const ResampleParams& P, void* workspace, cudaStre
                 P.M);
     long long grid = (long long)sms * WS_CTAS_PER_SM;
     if (grid > P.N) grid = P.N;
-    k_normalize_resample<true><<<(int)grid, NR_TPB, 0, stream>>>(P, static_cast<float*>(workspace));
+    k_normalize_resample<true, NR_TPB><<<(int)grid, NR_TPB, 0, stream>>>(P, static_cast<float*>(workspace));
     MMF_LAUNCH_CHECK("k_normalize_resample<global>");
+    return MMF_OK;
+  }
+  if (P.M <= NR_WARP_MAX_M && P.M_out <= 4 * NR_WARP_MAX_M) {
+    // warp per trajectory, 4 trajectories per CTA; the kernel is bound by the latency of one warp walking its
+    // trajectory, so what matters is that all trajectories are resident at once (no second, half-empty wave)
+    constexpr int per_cta = NR_WARP_TPB / 32;
+    const size_t smem4 = smem * per_cta;
+    int per_sm = (int)((200 * 1024) / (smem4 + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > NR_WARP_CTAS_PER_SM ? NR_WARP_CTAS_PER_SM : per_sm);
+    long long ctas = ((long long)P.N + per_cta - 1) / per_cta;
+    long long grid = (long long)sms * per_sm;
+    if (grid > ctas) grid = ctas;
+    k_normalize_resample<false, 32><<<(int)grid, NR_WARP_TPB, smem4, stream>>>(P, nullptr);
+    MMF_LAUNCH_CHECK("k_normalize_resample<warp>");
     return MMF_OK;
   }
   // enough CTAs per SM to hide the serial CDF chain of one trajectory behind the others
@@ -350,7 +548,7 @@ int launch_normalize_resample(const ResampleParams& P, void* workspace, cudaStre
   per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
   long long grid = (long long)sms * per_sm;
   if (grid > P.N) grid = P.N;
-  k_normalize_resample<false><<<(int)grid, NR_TPB, smem, stream>>>(P, nullptr);
+  k_normalize_resample<false, NR_TPB><<<(int)grid, NR_TPB, smem, stream>>>(P, nullptr);
   MMF_LAUNCH_CHECK("k_normalize_resample");
   return MMF_OK;
 }

@@ -64,6 +64,19 @@ class ImageEncoder(nn.Sequential):
             self.__dict__["_mmf_ws"] = ws
         return ws[1]
 
+    @staticmethod
+    def _split_tail(tail):
+        return len(tail) >= 2 and isinstance(tail[0], nn.Flatten) and isinstance(tail[1], nn.Linear)
+
+    @staticmethod
+    def _flatten_linear(h, linear):
+        """Flatten + Linear(C*1024 -> units) as one batched GEMM over the C channel slabs: the plain (n, 8192) x
+        (8192, 64) product gives the library only n/128 thread blocks; batching over channels gives C times more."""
+        n, C = h.shape[0], h.shape[1]
+        w = linear.weight.view(linear.out_features, C, 1024).permute(1, 2, 0)  # (C, 1024, units)
+        part = torch.bmm(h.view(n, C, 1024).transpose(0, 1), w)                 # (C, n, units)
+        return part.sum(dim=0) + linear.bias
+
     def forward(self, x):
         convs = self._trunk() if self.fused_trunk else None
         use_fused = (
@@ -91,7 +104,8 @@ class ImageEncoder(nn.Sequential):
             ops.enc_conv3x3(n, 32, 16, map_y, w3, relu=True, out_map=map_x)                    # Conv 32->16 + ReLU (reuses map_x)
             h = torch.empty((n, cout, 32, 32), device=x.device, dtype=torch.float32)
             ops.enc_conv3x3(n, 16, cout, map_x, w4, relu=False, out_nchw=h)                    # Conv 16->8
-            for layer in tail:
+            h = self._flatten_linear(h, tail[1]) if self._split_tail(tail) else tail[1](tail[0](h))
+            for layer in tail[2:]:
                 h = layer(h)
             outs.append(h)
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
