@@ -355,7 +355,8 @@ def main():
 
     def e2e_pass():
         with torch.no_grad():
-            o = {k: v.to(dev, non_blocking=True) for k, v in host_obs.items()}
+            # PF: forward_loop takes the pinned host observations and streams them in behind the encoders
+            o = host_obs if is_pf else {k: v.to(dev, non_blocking=True) for k, v in host_obs.items()}
             c = host_controls.to(dev, non_blocking=True)
             m0 = host_mean0.to(dev, non_blocking=True)
             filt.initialize_beliefs(mean=m0, covariance=cov)

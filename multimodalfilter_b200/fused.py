@@ -372,13 +372,50 @@ def flatten_time(observations, T, N):
     return {k: v.reshape(T * N, *v.shape[2:]) for k, v in observations.items()}
 
 
+class StagedObservations(dict):
+    """Observation dict whose (T, N, ...) tensors are being copied host -> device, chunk by chunk over the flattened
+    T*N rows, on a side stream.  ``ready(hi)`` makes the current stream wait until rows [0, hi) have landed, so the
+    encoders of chunk c run while chunk c+1 is still on the PCIe bus (end-to-end ``forward_loop`` from pinned host
+    buffers: the copy disappears behind the encoder kernels)."""
+
+    def __init__(self, host_observations, device, T, N, chunk_rows):
+        super().__init__()
+        self.chunk_rows = chunk_rows
+        self.events = []
+        total = T * N
+        side = torch.cuda.Stream(device=device)
+        flat_src = {}
+        for k, v in host_observations.items():
+            self[k] = torch.empty(v.shape, dtype=v.dtype, device=device)
+            flat_src[k] = v.reshape(total, *v.shape[2:])
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for lo in range(0, total, chunk_rows):
+                hi = min(total, lo + chunk_rows)
+                for k, dst in self.items():
+                    dst.reshape(total, *dst.shape[2:])[lo:hi].copy_(flat_src[k][lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                self.events.append(ev)
+        for dst in self.values():
+            dst.record_stream(side)
+
+    def ready(self, hi):
+        torch.cuda.current_stream().wait_event(self.events[(hi + self.chunk_rows - 1) // self.chunk_rows - 1])
+
+
 def batched_over_time(fn, observations, T, N, chunk_rows=16384):
     """Run a per-trajectory module once over all T*N rows (chunked to bound CNN activations)."""
     flat = flatten_time(observations, T, N)
     total = T * N
+    staged = isinstance(observations, StagedObservations)
+    if staged:
+        chunk_rows = observations.chunk_rows
     outs = []
     for lo in range(0, total, chunk_rows):
         hi = min(total, lo + chunk_rows)
+        if staged:
+            observations.ready(hi)
         outs.append(fn({k: v[lo:hi] for k, v in flat.items()}))
     return outs
 

@@ -267,7 +267,12 @@ class ParticleFilter(Filter):
         require_cuda(controls, "controls")
         T, N = controls.shape[:2]
         assert SliceWrapper(observations).shape[:2] == (T, N), "observations and controls disagree on (T, N)"
+        if all(isinstance(v, torch.Tensor) and v.device.type == "cpu" for v in observations.values()):
+            # host (pinned) observations: stream them in behind the encoders instead of copying first
+            observations = fused.StagedObservations(observations, controls.device, T, N, chunk_rows=16384)
         feats, modw = self.hoist_observations(plan, observations, T, N)
+        if isinstance(observations, fused.StagedObservations):
+            observations.ready(T * N)
         estimates = controls.new_zeros((T, N, self.state_dim), dtype=torch.float32)
         for t in range(T):
             hoisted = ([None if f is None else f[t] for f in feats], None if modw is None else modw[t])
@@ -293,6 +298,8 @@ class ParticleFilter(Filter):
                 chunks = fused.batched_over_time(lambda o: wm(observations=o), observations, T, N)
                 modw = torch.cat(chunks).reshape(T, N, -1).contiguous()
             else:
+                if isinstance(observations, fused.StagedObservations):
+                    observations.ready(T * N)
                 obs = SliceWrapper(observations)
                 modw = torch.stack([wm(observations=obs[t]) for t in range(T)]).contiguous()
         return feats, modw

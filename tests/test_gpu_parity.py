@@ -612,3 +612,22 @@ def test_image_encoder_module_fused_trunk_matches_torch_path(batch):
     # with autograd on the module is the plain torch Sequential (training path untouched)
     y = enc(x[:2])
     assert y.requires_grad
+
+
+def test_forward_loop_streams_host_observations():
+    """Pinned host observations are staged chunk by chunk behind the encoders; the result is that of device inputs."""
+    name, sd, N, Mp, T = "PushCrossmodalParticleFilter", 2, 6, 30, 5
+    init, eps, us = draw_noise(T, N, Mp, sd, seed=4)
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=5)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd).to(DEV).contiguous()
+    outs = []
+    for host in (False, True):
+        p = fill_parameters(_product(name)(), seed=23).to(DEV).eval()
+        p.num_particles = Mp
+        p.noise = ReplayNoise(init_eps=init, process_eps=eps, uniforms=us)
+        with torch.no_grad():
+            p.initialize_beliefs(mean=states[0].to(DEV), covariance=cov)
+            o = {k: (v[1:].contiguous().pin_memory() if host else v[1:].to(DEV)) for k, v in obs.items()}
+            outs.append(p.forward_loop(observations=o, controls=controls[1:].to(DEV)))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
