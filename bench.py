@@ -199,7 +199,7 @@ def bptt_arm(args):
         p.requires_grad_(False)
     for p in trainable:
         p.requires_grad_(True)
-    opt = torch.optim.Adam(trainable, lr=1e-4)
+    opt = torch.optim.Adam(trainable, lr=1e-4, fused=True)  # one multi-tensor kernel instead of ~10 launches per tensor
     g = torch.Generator(device=dev).manual_seed(rank)
     feats = [torch.randn(T, N, 64, device=dev, generator=g), torch.randn(T, N, 128, device=dev, generator=g)]
     wm_feats = torch.randn(T, N, 192, device=dev, generator=g)
@@ -250,7 +250,7 @@ def bptt_arm(args):
             "vs_baseline": None, "dtype": filt.precision, "data": "synthetic",
             "config": {"workload": cfg, "id": "c4", "model": name, "trajectories_per_gpu": N, "particles": Mp,
                        "filter_steps_per_pass": T, "phases": "forward + backward + grad all-reduce + Adam",
-                       "encoders": "hoisted and frozen (features are inputs)", "final_loss": float(loss)},
+                       "encoders": "hoisted and frozen (features are inputs)", "final_loss": float(loss.detach())},
             "clocks": clk.summary(), "gpu_launches": prof["launches"], "kernels": kern,
             "e2e": {"value": world * units / (ms / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 4, "note": "training step is device-resident; loss scalar read back"},

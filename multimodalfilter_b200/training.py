@@ -42,7 +42,11 @@ def _grads_for_head(spec, act, delta, dW, d_ll, moved_flat):
     (in_lin, pre), (mid, post, out) = spec.state, spec.shared
     L = 2 * len(pre) + 1 + 2 * len(post)
     db = delta.sum(dim=1)  # (L+1, 64)
-    grads = [delta[L].t() @ moved_flat, db[L]]
+    # reductions over the P = N*M rows with a handful of output columns: gemv (bandwidth-bound) instead of a GEMM
+    # whose K = P dimension sends the library to a slow SIMT split
+    sd = moved_flat.shape[1]
+    g_in = torch.stack([torch.mv(delta[L].t(), moved_flat[:, d].contiguous()) for d in range(sd)], dim=1)
+    grads = [g_in, db[L]]
     layer = 0
     for _ in pre:
         for _half in range(2):
@@ -57,7 +61,7 @@ def _grads_for_head(spec, act, delta, dW, d_ll, moved_flat):
         for _half in range(2):
             grads += [dW[layer], db[layer]]
             layer += 1
-    grads += [(d_ll[None, :] @ act[L]), d_ll.sum().reshape(1)]
+    grads += [torch.mv(act[L].t(), d_ll)[None, :], d_ll.sum().reshape(1)]
     return grads, mid_layer
 
 
