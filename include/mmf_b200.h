@@ -240,10 +240,19 @@ int mmf_pf_heads_backward(const mmf_pf_model* model, int32_t N, int32_t M, const
  *   mmf_enc_stem      Conv2d(1, 32, 5, padding=2) + ReLU; w = weight as [tap 25][32] then bias[32], fp32.
  *   mmf_enc_conv3x3   Conv2d(cin, cout, 3, padding=1) [+ residual map] [+ ReLU] on the tensor cores
  *                     (bf16 hi/lo split operands, fp32 accumulation); (cin, cout) in {(32,32), (32,16), (16,<=16)}.
- *                     w_image = bf16 [hi|lo][tap 9][cin/8][npad][8] then fp32 bias[npad], npad = 32 if cout > 16
- *                     else 16 (rows >= cout zero).  Writes out_map (planes, npad channels) and/or out_nchw
+ *                     w_image = bf16 [tap 9][cin/8][2 npad rows: hi then lo][8] then fp32 bias[npad], npad = 32
+ *                     if cout > 16 else 16 (rows >= cout zero).  Writes out_map (planes, npad channels) and/or out_nchw
  *                     (n_images, cout, 32, 32) fp32. */
 size_t mmf_enc_map_bytes(int32_t channels);
+/*   mmf_enc_trunk     the whole trunk (stem, residual block, 32->16, 16->cout) of every image in ONE launch: a
+ *                     persistent CTA carries an image through all layers, its activation maps live in `scratch`
+ *                     (mmf_enc_trunk_scratch_bytes() bytes, zero-initialised once by the caller; stays L2-resident).
+ *                     weights = [w_image block1 | w_image block2 | w_image 32->16 | w_image 16->cout | stem w],
+ *                     each as described above (mmf_enc_trunk_weight_bytes() bytes in total). */
+size_t mmf_enc_trunk_scratch_bytes(void);
+size_t mmf_enc_trunk_weight_bytes(void);
+int mmf_enc_trunk(int32_t n_images, int32_t cout, const float* images, const void* weights, void* scratch,
+                  float* out_nchw, void* stream);
 int mmf_enc_stem(int32_t n_images, const float* images, const float* w, void* out_map, void* stream);
 int mmf_enc_conv3x3(int32_t n_images, int32_t cin, int32_t cout, const void* in_map, const void* w_image,
                     const void* res_map, int32_t relu, void* out_map, float* out_nchw, void* stream);

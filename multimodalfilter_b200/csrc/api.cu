@@ -299,4 +299,15 @@ int mmf_enc_conv3x3(int32_t n_images, int32_t cin, int32_t cout, const void* in_
   return launch_enc_conv3x3(n_images, cin, cout, in_map, w_image, res_map, relu, out_map, out_nchw, (cudaStream_t)stream);
 }
 
+size_t mmf_enc_trunk_scratch_bytes(void) { return enc_trunk_scratch_bytes(); }
+size_t mmf_enc_trunk_weight_bytes(void) { return enc_trunk_weight_bytes(); }
+
+int mmf_enc_trunk(int32_t n_images, int32_t cout, const float* images, const void* weights, void* scratch,
+                  float* out_nchw, void* stream) {
+  MMF_REQUIRE(n_images >= 0 && cout >= 1 && cout <= 16, "enc_trunk: bad shape n=%d cout=%d", n_images, cout);
+  MMF_REQUIRE(n_images == 0 || (images && weights && scratch && out_nchw), "enc_trunk: NULL buffer");
+  MMF_REQUIRE((((uintptr_t)weights | (uintptr_t)scratch) & 15) == 0, "enc_trunk: weights and scratch must be 16-byte aligned");
+  return launch_enc_trunk(n_images, cout, images, weights, scratch, out_nchw, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -14,8 +14,10 @@
 //     brought into shared memory by bulk async copies (TMA), and the A operand of tap (dy, dx) is that same
 //     shared memory addressed through a no-swizzle K-major UMMA descriptor whose start address is shifted by
 //     34 dy + dx positions: no im2col, no gather instructions at all;
-//   * D[128 positions x Cout] += A_tap[128 x Cin] * W_tap[Cin x Cout] for the 9 taps, three bf16 MMAs per K
-//     step (hi*hi + lo*hi + hi*lo), accumulated in TMEM in fp32;
+//   * D[128 positions x Cout] += A_tap[128 x Cin] * W_tap[Cin x Cout] for the 9 taps with split operands
+//     (hi*hi + hi*lo + lo*hi).  The MMAs read A from shared memory and are bound by that traffic, so W_hi and W_lo
+//     are stacked along N: ONE MMA A_hi x [W_hi | W_lo] (N = 2 Cout) yields both products from one pass over A_hi,
+//     a second A_lo x W_hi adds the third; the epilogue sums the two column halves.  fp32 accumulation in TMEM;
 //   * warp-specialised pipeline: warp 0 = TMA producer, warp 1 = MMA issuer, warps 4-11 = two epilogue groups
 //     (bias, residual, ReLU, bf16 split, coalesced 16-byte plane stores), 4 stages of shared memory / TMEM.
 // The 5x5 stem (one input channel, 1.6 MFLOP per image) runs on the CUDA cores and emits the first map.
@@ -34,6 +36,7 @@ constexpr int ENC_WIN_POS = 128 + 2 * ENC_HALO;  // 208 positions per plane in a
 constexpr int ENC_WIN_B = ENC_WIN_POS * 16;      // 3328 B
 constexpr int ENC_STAGES = 4;
 constexpr int ENC_THREADS = 384;
+constexpr int ENC_DCOLS = 64;                 // TMEM columns per stage: [hi*hi + lo*hi | hi*lo] halves of up to 32 channels
 
 __host__ __device__ inline size_t enc_map_bytes(int channels) { return (size_t)(channels / 8) * 2 * ENC_PLANE_B; }
 
@@ -139,10 +142,50 @@ __global__ void __launch_bounds__(256) k_enc_stem(const float* __restrict__ imag
   }
 }
 
+// this thread's accumulator row: columns [0, NPAD) hold hi*hi + lo*hi, [NPAD, 2 NPAD) hold hi*lo -> their sum
+template <int NPAD>
+__device__ __forceinline__ void load_accumulator(uint32_t taddr, uint32_t (&d)[NPAD]) {
+  uint32_t e[NPAD];
+#pragma unroll
+  for (int c = 0; c < NPAD; c += 16) {
+    tmem_ld16(taddr + c, reinterpret_cast<uint32_t(&)[16]>(d[c]));
+    tmem_ld16(taddr + NPAD + c, reinterpret_cast<uint32_t(&)[16]>(e[c]));
+  }
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < NPAD; ++c) d[c] = __float_as_uint(__uint_as_float(d[c]) + __uint_as_float(e[c]));
+}
+
+template <int CIN, int NPAD>
+__device__ __forceinline__ void issue_conv(uint32_t st_addr, uint32_t w_addr, uint32_t d) {
+  constexpr int KC = CIN / 8;
+  constexpr uint32_t IDESC2 = make_idesc(2 * NPAD, 128);  // A_hi x [W_hi | W_lo]
+  constexpr uint32_t IDESC1 = make_idesc(NPAD, 128);      // A_lo x W_hi
+  uint32_t acc = 0;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int shift = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1);
+#pragma unroll
+    for (int ks = 0; ks < CIN / 16; ++ks) {
+      // A: plane (chunk 2 ks, hi|lo) at the shifted position; the second K chunk is the next chunk's plane
+      const uint32_t a_hi = st_addr + (uint32_t)((2 * ks) * 2) * ENC_WIN_B + (uint32_t)shift * 16;
+      const uint32_t a_lo = a_hi + ENC_WIN_B;
+      const uint64_t da_hi = make_desc_interleave(a_hi, 2 * ENC_WIN_B, 128);
+      const uint64_t da_lo = make_desc_interleave(a_lo, 2 * ENC_WIN_B, 128);
+      // B: [tap][chunk][2 NPAD rows][8]; rows [0, NPAD) = W_hi, [NPAD, 2 NPAD) = W_lo
+      const uint32_t b = w_addr + (uint32_t)((tap * KC + 2 * ks) * 2 * NPAD) * 16;
+      const uint64_t db = make_desc_interleave(b, 2 * NPAD * 16, 128);
+      mma_ss(d, da_hi, db, IDESC2, acc);  // columns [0, NPAD) += hi*hi, [NPAD, 2 NPAD) += hi*lo
+      mma_ss(d, da_lo, db, IDESC1, 1);    // columns [0, NPAD) += lo*hi
+      acc = 1;
+    }
+  }
+}
+
 // ---- 3x3 convolution as implicit GEMM on tcgen05 -----------------------------------------------------------
 struct ConvParams {
   const uint8_t* in_map;    // CIN channels
-  const uint8_t* w_image;   // [hi|lo][tap 9][chunk CIN/8][NPAD rows][8] bf16, then bias fp32[NPAD]
+  const uint8_t* w_image;   // [tap 9][chunk CIN/8][2 NPAD rows: hi then lo][8] bf16, then bias fp32[NPAD]
   const uint8_t* res_map;   // residual input (same channel count as the output) or null
   uint8_t* out_map;         // bf16 hi/lo planes of NPAD channels, or null
   float* out_nchw;          // (n_images, cout, 32, 32) fp32, or null
@@ -155,7 +198,6 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_conv3x3(const __grid_con
   constexpr int PLANES = KC * 2;
   constexpr int STAGE_B = PLANES * ENC_WIN_B;
   constexpr int W_B = 2 * 9 * KC * NPAD * 16;
-  constexpr uint32_t IDESC = make_idesc(NPAD, 128);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;                                         // W_B bytes + bias
   float* bias_s = reinterpret_cast<float*>(smem + W_B);
@@ -182,7 +224,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_conv3x3(const __grid_con
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(ENC_STAGES * 32)
+                 "r"(ENC_STAGES * ENC_DCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -230,29 +272,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_conv3x3(const __grid_con
         mbar_wait(full + s, par);
         tc_fence_after();
         const uint32_t st_addr = smem_u32(stage0 + s * STAGE_B);
-        const uint32_t d = tmem_base + s * 32;
-        uint32_t acc = 0;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int shift = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1);
-#pragma unroll
-          for (int ks = 0; ks < CIN / 16; ++ks) {
-            // A: plane (chunk 2 ks, hi|lo) at the shifted position; the second K chunk is the next chunk's plane
-            const uint32_t a_hi = st_addr + (uint32_t)((2 * ks) * 2) * ENC_WIN_B + (uint32_t)shift * 16;
-            const uint32_t a_lo = a_hi + ENC_WIN_B;
-            const uint64_t da_hi = make_desc_interleave(a_hi, 2 * ENC_WIN_B, 128);
-            const uint64_t da_lo = make_desc_interleave(a_lo, 2 * ENC_WIN_B, 128);
-            // B: [hi|lo][tap][chunk][NPAD][8]
-            const uint32_t b_hi = w_addr + (uint32_t)((tap * KC + 2 * ks) * NPAD) * 16;
-            const uint32_t b_lo = b_hi + 9 * KC * NPAD * 16;
-            const uint64_t db_hi = make_desc_interleave(b_hi, NPAD * 16, 128);
-            const uint64_t db_lo = make_desc_interleave(b_lo, NPAD * 16, 128);
-            mma_ss(d, da_hi, db_hi, IDESC, acc);
-            acc = 1;
-            mma_ss(d, da_lo, db_hi, IDESC, 1);
-            mma_ss(d, da_hi, db_lo, IDESC, 1);
-          }
-        }
+        const uint32_t d = tmem_base + s * ENC_DCOLS;
+        issue_conv<CIN, NPAD>(st_addr, w_addr, d);
         tc_commit(mma_done + s);
         tc_commit(stage_free + s);
       }
@@ -275,10 +296,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_conv3x3(const __grid_con
       mbar_wait(mma_done + s, par);
       tc_fence_after();
       uint32_t d[NPAD];
-      const uint32_t taddr = tmem_base + s * 32 + ((uint32_t)(quad * 32) << 16);
-      tmem_ld16(taddr, reinterpret_cast<uint32_t(&)[16]>(d[0]));
-      if (NPAD == 32) tmem_ld16(taddr + 16, reinterpret_cast<uint32_t(&)[16]>(d[NPAD - 16]));
-      tc_wait_ld();
+      const uint32_t taddr = tmem_base + s * ENC_DCOLS + ((uint32_t)(quad * 32) << 16);
+      load_accumulator<NPAD>(taddr, d);
       tc_fence_before();
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(tmem_free + s);  // D[s] may be overwritten by the item after next
@@ -321,7 +340,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_conv3x3(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ENC_STAGES * 32) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ENC_STAGES * ENC_DCOLS) : "memory");
   }
 }
 
@@ -345,6 +364,309 @@ static int launch_conv(const ConvParams& P, cudaStream_t stream) {
   if (grid > sms) grid = sms;
   k_enc_conv3x3<CIN, NPAD><<<(unsigned)grid, ENC_THREADS, smem, stream>>>(P);
   MMF_LAUNCH_CHECK("k_enc_conv3x3");
+  return MMF_OK;
+}
+
+// ---- fused trunk: all five layers of one image by one CTA, activation maps in L2-resident scratch ---------------
+// The layer-by-layer kernels above stream every map through HBM (ncu: 3.7 TB/s, 57 % of peak, tensor pipe 26 %).
+// Here a persistent CTA carries an image through stem -> block1 -> block2(+x) -> 32->16 -> 16->8 by itself: its three
+// scratch maps (480 KB) are private, so 148 CTAs keep 71 MB hot in the 126 MB L2 and HBM only sees the raw image and
+// the final (8, 32, 32) activations.  Work items = (layer, tile) in order; tile t of layer l+1 only needs tiles
+// t-1..t+1 of layer l, tracked by one mbarrier per (layer, tile), so the TMA -> MMA -> epilogue ring never drains
+// between layers.  Epilogue warps write the maps with generic stores and publish them to the async proxy
+// (fence.proxy.async.global + mbarrier release) before the producer's bulk copies read them.
+constexpr int TR_LAYERS = 5;                    // 0 = stem (CUDA cores), 1..4 = 3x3 convolutions
+constexpr int TR_CONV_ITEMS = 4 * ENC_TILES;    // per image
+constexpr int TR_STAGE_B = 8 * ENC_WIN_B;       // a stage holds the widest window (32 channels)
+constexpr int TR_W2_B = 2 * 9 * 4 * 32 * 16 + 128;   // 32->32: operand image + bias
+constexpr int TR_W3_B = 2 * 9 * 4 * 16 * 16 + 64;    // 32->16
+constexpr int TR_W4_B = 2 * 9 * 2 * 16 * 16 + 64;    // 16->(<=16)
+constexpr int TR_WSTEM_B = (25 * 32 + 32) * 4;
+constexpr int TR_W_B = 2 * TR_W2_B + TR_W3_B + TR_W4_B + TR_WSTEM_B;
+
+struct TrunkParams {
+  const float* images;      // (n, 32, 32)
+  const uint8_t* weights;   // [W block1 | W block2 | W 32->16 | W 16->8 | stem fp32], as packed for the layer kernels
+  uint8_t* scratch;         // gridDim.x * 3 * enc_map_bytes(32), zero-initialised once
+  float* out_nchw;          // (n, cout, 32, 32)
+  int n_images, cout;
+};
+
+__device__ __forceinline__ void publish_tile(uint64_t* bar) {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
+// accumulator row -> bias (+ residual) (+ ReLU) -> planes in `out_map` or NCHW fp32
+template <int NPAD>
+__device__ __forceinline__ void epilogue_conv(const uint32_t (&d)[32], const float* bias_s, const uint8_t* res_map,
+                                              bool relu, bool valid, int pos, uint8_t* out_map, float* out_img, int cout) {
+  const size_t plane_off = (size_t)(ENC_GUARD + pos) * 16;
+#pragma unroll
+  for (int kc = 0; kc < NPAD / 8; ++kc) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(d[kc * 8 + j]) + bias_s[kc * 8 + j];
+    if (res_map != nullptr) {
+      const uint8_t* rp = res_map + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
+      float x[8];
+      unpack8(*reinterpret_cast<const uint4*>(rp), *reinterpret_cast<const uint4*>(rp + ENC_PLANE_B), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += x[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (relu) v[j] = fmaxf(v[j], 0.0f);
+      if (!valid) v[j] = 0.0f;
+    }
+    if (out_map != nullptr) {
+      uint4 hi4, lo4;
+      split8(v, hi4, lo4);
+      uint8_t* op = out_map + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
+      *reinterpret_cast<uint4*>(op) = hi4;
+      *reinterpret_cast<uint4*>(op + ENC_PLANE_B) = lo4;
+    }
+    if (out_img != nullptr && valid) {
+      const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (kc * 8 + j < cout) out_img[((size_t)(kc * 8 + j) * 32 + y) * 32 + x] = v[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_constant__ TrunkParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* w_s = smem;
+  uint8_t* stage0 = smem + ((TR_W_B + 127) & ~127);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + ENC_STAGES * TR_STAGE_B);
+  uint64_t* full = bars;
+  uint64_t* mma_done = bars + ENC_STAGES;
+  uint64_t* stage_free = bars + 2 * ENC_STAGES;
+  uint64_t* tmem_free = bars + 3 * ENC_STAGES;
+  uint64_t* wbar = bars + 4 * ENC_STAGES;
+  uint64_t* tile_done = wbar + 1;  // [layer 0..3][tile]: that tile of the layer's OUTPUT map is written and published
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 4 * ENC_TILES);
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (tid == 0) {
+    for (int s = 0; s < ENC_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(mma_done + s, 1);
+      mbar_init(stage_free + s, 1);
+      mbar_init(tmem_free + s, 4);
+    }
+    for (int i = 0; i < 4 * ENC_TILES; ++i) mbar_init(tile_done + i, 4);
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(ENC_STAGES * ENC_DCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const size_t map32 = enc_map_bytes(32);
+  uint8_t* sx = P.scratch + (size_t)blockIdx.x * 3 * map32;  // stem output x, later the 16-channel map z
+  uint8_t* st = sx + map32;                                   // block1 output
+  uint8_t* sy = st + map32;                                   // resblock output
+  // shared-memory offsets of the per-layer weights
+  constexpr int OFF_W[5] = {2 * TR_W2_B + TR_W3_B + TR_W4_B, 0, TR_W2_B, 2 * TR_W2_B, 2 * TR_W2_B + TR_W3_B};
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (elect_one_sync()) {
+      mbar_expect_tx(wbar, TR_W_B);
+      for (uint32_t off = 0; off < (uint32_t)TR_W_B; off += 32768) {
+        const uint32_t n = (uint32_t)TR_W_B - off < 32768 ? (uint32_t)TR_W_B - off : 32768;
+        bulk_g2s(w_s + off, P.weights + off, n, wbar);
+      }
+      long long c = 0;
+      int k = 0;
+      for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x, ++k) {
+        const uint32_t ipar = (uint32_t)(k & 1);
+        for (int layer = 1; layer <= 4; ++layer) {
+          const uint8_t* in = layer == 1 ? sx : layer == 2 ? st : layer == 3 ? sy : sx;
+          const int planes = layer == 4 ? 4 : 8;
+          for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
+            const int s = (int)(c % ENC_STAGES);
+            const uint32_t par = (uint32_t)((c / ENC_STAGES) & 1);
+            mbar_wait(stage_free + s, par ^ 1u);
+            // the window reaches into the neighbouring tiles of the producing layer
+            const uint64_t* dep = tile_done + (layer - 1) * ENC_TILES;
+            if (tile > 0) mbar_wait(const_cast<uint64_t*>(dep) + tile - 1, ipar);
+            mbar_wait(const_cast<uint64_t*>(dep) + tile, ipar);
+            if (tile + 1 < ENC_TILES) mbar_wait(const_cast<uint64_t*>(dep) + tile + 1, ipar);
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            const uint8_t* src = in + (size_t)(ENC_GUARD + tile * 128 - ENC_HALO) * 16;
+            mbar_expect_tx(full + s, (uint32_t)planes * ENC_WIN_B);
+            for (int pl = 0; pl < planes; ++pl)
+              bulk_g2s(stage0 + s * TR_STAGE_B + pl * ENC_WIN_B, src + (size_t)pl * ENC_PLANE_B, ENC_WIN_B, full + s);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------------------------------- MMA issuer
+    mbar_wait(wbar, 0);
+    if (elect_one_sync()) {
+      const uint32_t w_addr = smem_u32(w_s);
+      long long c = 0;
+      for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
+        for (int layer = 1; layer <= 4; ++layer) {
+          for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
+            const int s = (int)(c % ENC_STAGES);
+            const uint32_t par = (uint32_t)((c / ENC_STAGES) & 1);
+            mbar_wait(tmem_free + s, par ^ 1u);
+            mbar_wait(full + s, par);
+            tc_fence_after();
+            const uint32_t st_addr = smem_u32(stage0 + s * TR_STAGE_B);
+            const uint32_t d = tmem_base + s * ENC_DCOLS;
+            if (layer <= 2) issue_conv<32, 32>(st_addr, w_addr + OFF_W[layer], d);
+            else if (layer == 3) issue_conv<32, 16>(st_addr, w_addr + OFF_W[3], d);
+            else issue_conv<16, 16>(st_addr, w_addr + OFF_W[4], d);
+            tc_commit(mma_done + s);
+            tc_commit(stage_free + s);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue groups (and the stem on the CUDA cores)
+    const int eg = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + (tid & 31);
+    mbar_wait(wbar, 0);
+    const float* wstem = reinterpret_cast<const float*>(w_s + OFF_W[0]);
+    long long g = 0, c = 0;
+    for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
+      const float* im = P.images + (size_t)image * 1024;
+      for (int layer = 0; layer < TR_LAYERS; ++layer) {
+        for (int tile = 0; tile < ENC_TILES; ++tile, ++g) {
+          const long long cc = c;
+          if (layer > 0) ++c;
+          if ((int)(g & 1) != eg) continue;
+          const int pos = tile * 128 + r;
+          const bool valid = enc_valid(pos);
+          if (layer == 0) {
+            float acc[32];
+#pragma unroll
+            for (int ch = 0; ch < 32; ++ch) acc[ch] = wstem[25 * 32 + ch];
+            if (valid) {
+              const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
+              for (int ky = 0; ky < 5; ++ky) {
+                const int yy = y + ky - 2;
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                  const int xx = x + kx - 2;
+                  const float p = (yy >= 0 && yy < 32 && xx >= 0 && xx < 32) ? __ldg(im + yy * 32 + xx) : 0.0f;
+                  const float4* w4 = reinterpret_cast<const float4*>(wstem + (ky * 5 + kx) * 32);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 t = w4[q];
+                    acc[4 * q] = fmaf(t.x, p, acc[4 * q]);
+                    acc[4 * q + 1] = fmaf(t.y, p, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(t.z, p, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(t.w, p, acc[4 * q + 3]);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = valid ? fmaxf(acc[kc * 8 + j], 0.0f) : 0.0f;
+              uint4 hi4, lo4;
+              split8(v, hi4, lo4);
+              uint8_t* plane = sx + (size_t)(kc * 2) * ENC_PLANE_B + (size_t)(ENC_GUARD + pos) * 16;
+              *reinterpret_cast<uint4*>(plane) = hi4;
+              *reinterpret_cast<uint4*>(plane + ENC_PLANE_B) = lo4;
+            }
+            publish_tile(tile_done + tile);
+            continue;
+          }
+          const int s = (int)(cc % ENC_STAGES);
+          const uint32_t par = (uint32_t)((cc / ENC_STAGES) & 1);
+          mbar_wait(mma_done + s, par);
+          tc_fence_after();
+          uint32_t d[32];
+          const uint32_t taddr = tmem_base + s * ENC_DCOLS + ((uint32_t)(quad * 32) << 16);
+          if (layer <= 2) load_accumulator<32>(taddr, d);
+          else load_accumulator<16>(taddr, reinterpret_cast<uint32_t(&)[16]>(d[0]));
+          tc_fence_before();
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(tmem_free + s);
+          const float* bias_s = reinterpret_cast<const float*>(
+              w_s + OFF_W[layer] + (layer <= 2 ? TR_W2_B - 128 : layer == 3 ? TR_W3_B - 64 : TR_W4_B - 64));
+          if (layer == 1) epilogue_conv<32>(d, bias_s, nullptr, true, valid, pos, st, nullptr, 0);
+          else if (layer == 2) epilogue_conv<32>(d, bias_s, sx, true, valid, pos, sy, nullptr, 0);
+          else if (layer == 3) epilogue_conv<16>(d, bias_s, nullptr, true, valid, pos, sx, nullptr, 0);
+          else epilogue_conv<16>(d, bias_s, nullptr, false, valid, pos, nullptr, P.out_nchw + (size_t)image * P.cout * 1024, P.cout);
+          if (layer < 4) publish_tile(tile_done + layer * ENC_TILES + tile);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ENC_STAGES * ENC_DCOLS) : "memory");
+  }
+}
+
+static int trunk_grid(int* grid_out) {
+  int dev = 0, sms = 148;
+  MMF_CUDA(cudaGetDevice(&dev));
+  MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  *grid_out = sms;
+  return MMF_OK;
+}
+
+size_t enc_trunk_weight_bytes() { return TR_W_B; }
+
+size_t enc_trunk_scratch_bytes() {
+  int grid = 148;
+  trunk_grid(&grid);
+  return (size_t)grid * 3 * enc_map_bytes(32);
+}
+
+int launch_enc_trunk(int n_images, int cout, const float* images, const void* weights, void* scratch, float* out_nchw,
+                     cudaStream_t stream) {
+  if (n_images == 0) return MMF_OK;
+  TrunkParams P;
+  P.images = images;
+  P.weights = static_cast<const uint8_t*>(weights);
+  P.scratch = static_cast<uint8_t*>(scratch);
+  P.out_nchw = out_nchw;
+  P.n_images = n_images;
+  P.cout = cout;
+  const size_t smem = ((TR_W_B + 127) & ~127) + (size_t)ENC_STAGES * TR_STAGE_B + 1024;
+  static thread_local int configured_dev = -1;
+  static thread_local size_t window = 0;
+  int dev = 0, grid = 148;
+  MMF_CUDA(cudaGetDevice(&dev));
+  int rc = trunk_grid(&grid);
+  if (rc) return rc;
+  if (configured_dev != dev) {
+    rc = opt_in_shared_memory(k_enc_trunk, &window);
+    if (rc) return rc;
+    configured_dev = dev;
+  }
+  MMF_REQUIRE(smem <= window, "encoder trunk needs %zu B of shared memory (window %zu B)", smem, window);
+  if (grid > n_images) grid = n_images;
+  k_enc_trunk<<<grid, ENC_THREADS, smem, stream>>>(P);
+  MMF_LAUNCH_CHECK("k_enc_trunk");
   return MMF_OK;
 }
 

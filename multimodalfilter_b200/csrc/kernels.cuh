@@ -60,6 +60,10 @@ int launch_head_chain_bwd(const mmf_pf_model* model, int N, int M, const float* 
                           float* delta_out, cudaStream_t stream);
 int launch_heads_dw(int K, int L, long long P, const float* act, const float* delta, float* dW, cudaStream_t stream);
 size_t enc_map_bytes_host(int channels);
+size_t enc_trunk_weight_bytes();
+size_t enc_trunk_scratch_bytes();
+int launch_enc_trunk(int n_images, int cout, const float* images, const void* weights, void* scratch, float* out_nchw,
+                     cudaStream_t stream);
 int launch_enc_stem(int n_images, const float* images, const float* w, void* out_map, cudaStream_t stream);
 int launch_enc_conv3x3(int n_images, int cin, int cout, const void* in_map, const void* w_image, const void* res_map,
                        int relu, void* out_map, float* out_nchw, cudaStream_t stream);

@@ -2,9 +2,8 @@
 
 ``ImageEncoder`` IS the reference's ``nn.Sequential`` (same children, same ``state_dict`` keys:
 ref: crossmodal/push_models/layers.py:93-104, crossmodal/door_models/layers.py:43-63); only its forward
-changes: under ``torch.no_grad()`` on a CUDA device the Conv2d layers run through ``mmf_enc_stem`` /
-``mmf_enc_conv3x3`` (tensor cores, bf16 hi/lo split operands, fp32 accumulation) and the Flatten/Linear tail
-stays with torch.  With autograd enabled (encoder training / pre-training) the plain module path runs, so
+changes: under ``torch.no_grad()`` on a CUDA device the Conv2d layers run through ``mmf_enc_trunk`` (one launch,
+tensor cores, bf16 hi/lo split operands, fp32 accumulation) and the Flatten/Linear tail stays with torch.  With autograd enabled (encoder training / pre-training) the plain module path runs, so
 gradients are untouched.  There is no CPU variant of the fused trunk: on a CPU tensor the module is the
 ordinary torch Sequential, exactly as in the reference.
 """
@@ -14,7 +13,7 @@ import torch.nn as nn
 from . import ops
 from .fannypack.nn import resblocks
 
-CHUNK_IMAGES = 4096  # images per pass of the trunk: bounds the activation-map workspace to ~2.2 GB
+CHUNK_IMAGES = 16384  # images per launch of the trunk: bounds the (n, 8, 32, 32) fp32 output to 0.5 GB
 
 
 def _is(m, cls, **attrs):
@@ -51,16 +50,14 @@ class ImageEncoder(nn.Sequential):
         key = tuple((p.data_ptr(), p._version) for c in convs for p in (c.weight, c.bias)) + (str(device),)
         cache = self.__dict__.get("_mmf_packed")
         if cache is None or cache[0] != key:
-            packed = [ops.enc_pack_stem(convs[0])] + [ops.enc_pack_conv3x3(c) for c in convs[1:]]
-            cache = (key, packed)
+            cache = (key, ops.enc_pack_trunk(convs))
             self.__dict__["_mmf_packed"] = cache
         return cache[1]
 
-    def _workspace(self, device):
+    def _scratch(self, device):
         ws = self.__dict__.get("_mmf_ws")
         if ws is None or ws[0] != str(device):
-            maps = [ops.enc_new_map(CHUNK_IMAGES, 32, device) for _ in range(3)]
-            ws = (str(device), maps)
+            ws = (str(device), ops.enc_trunk_scratch(device))  # zeroed once: the kernels never write the guards
             self.__dict__["_mmf_ws"] = ws
         return ws[1]
 
@@ -89,21 +86,15 @@ class ImageEncoder(nn.Sequential):
         )
         if not use_fused:
             return super().forward(x)
-        w_stem, w2a, w2b, w3, w4 = self._packed(convs, x.device)
-        map_x, map_t, map_y = self._workspace(x.device)
+        weights = self._packed(convs, x.device)
+        scratch = self._scratch(x.device)
         cout = convs[4].out_channels
         tail = list(self.children())[6:]
         outs = []
         images = x.reshape(-1, 32, 32).contiguous()
         for lo in range(0, images.shape[0], CHUNK_IMAGES):
-            chunk = images[lo:lo + CHUNK_IMAGES]
-            n = chunk.shape[0]
-            ops.enc_stem(chunk, w_stem, map_x)                                                # Conv 5x5 + ReLU
-            ops.enc_conv3x3(n, 32, 32, map_x, w2a, relu=True, out_map=map_t)                   # resblock.block1 + ReLU
-            ops.enc_conv3x3(n, 32, 32, map_t, w2b, res_map=map_x, relu=True, out_map=map_y)    # block2 + x, ReLU
-            ops.enc_conv3x3(n, 32, 16, map_y, w3, relu=True, out_map=map_x)                    # Conv 32->16 + ReLU (reuses map_x)
-            h = torch.empty((n, cout, 32, 32), device=x.device, dtype=torch.float32)
-            ops.enc_conv3x3(n, 16, cout, map_x, w4, relu=False, out_nchw=h)                    # Conv 16->8
+            # one launch: a persistent CTA carries each image through all five layers (maps stay in L2)
+            h = ops.enc_trunk(images[lo:lo + CHUNK_IMAGES], weights, scratch, cout)
             h = self._flatten_linear(h, tail[1]) if self._split_tail(tail) else tail[1](tail[0](h))
             for layer in tail[2:]:
                 h = layer(h)

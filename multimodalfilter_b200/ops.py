@@ -165,7 +165,7 @@ def enc_pack_stem(conv) -> torch.Tensor:
 
 
 def enc_pack_conv3x3(conv) -> torch.Tensor:
-    """Conv2d(cin, cout, 3) -> bf16 [hi|lo][tap][cin/8][npad][8] + fp32 bias[npad] as one byte tensor."""
+    """Conv2d(cin, cout, 3) -> bf16 [tap][cin/8][2 npad: hi rows then lo rows][8] + fp32 bias[npad] as one byte tensor."""
     w = conv.weight.detach().float()
     cout, cin = w.shape[0], w.shape[1]
     npad = 32 if cout > 16 else 16
@@ -177,7 +177,8 @@ def enc_pack_conv3x3(conv) -> torch.Tensor:
     def layout(t):  # (npad, cin, 3, 3) -> (tap, cin/8, npad, 8)
         return t.permute(2, 3, 1, 0).reshape(9, cin // 8, 8, npad).permute(0, 1, 3, 2).contiguous()
 
-    img = torch.stack([layout(hi), layout(lo)]).contiguous().view(torch.uint8).reshape(-1)
+    # rows [0, npad) = hi, [npad, 2 npad) = lo: one MMA over the stacked rows yields a*w_hi and a*w_lo together
+    img = torch.cat([layout(hi), layout(lo)], dim=2).contiguous().view(torch.uint8).reshape(-1)
     bias = torch.zeros(npad, device=w.device)
     bias[:cout] = conv.bias.detach().float()
     return torch.cat([img, bias.view(torch.uint8).reshape(-1)]).contiguous()
@@ -195,6 +196,29 @@ def enc_conv3x3(n_images, cin, cout, in_map, w_image, *, res_map=None, relu=True
     _lib.check(PROFILE.run("enc_conv3x3", 1, lib.mmf_enc_conv3x3, n_images, cin, cout, _lib.ptr(in_map),
                            _lib.ptr(w_image), _lib.ptr(res_map), int(relu), _lib.ptr(out_map), _lib.ptr(out_nchw),
                            _lib.stream_of(in_map)))
+
+
+def enc_pack_trunk(convs) -> torch.Tensor:
+    """[stem, block1, block2, 32->16, 16->cout] Conv2d modules -> the weight buffer of mmf_enc_trunk."""
+    stem, c2a, c2b, c3, c4 = convs
+    buf = torch.cat([enc_pack_conv3x3(c2a), enc_pack_conv3x3(c2b), enc_pack_conv3x3(c3), enc_pack_conv3x3(c4),
+                     enc_pack_stem(stem).view(torch.uint8).reshape(-1)]).contiguous()
+    assert buf.numel() == int(_lib.load().mmf_enc_trunk_weight_bytes())
+    return buf
+
+
+def enc_trunk_scratch(device) -> torch.Tensor:
+    return torch.zeros(int(_lib.load().mmf_enc_trunk_scratch_bytes()), dtype=torch.uint8, device=device)
+
+
+def enc_trunk(images, weights, scratch, cout):
+    """images (n, 32, 32) fp32 -> (n, cout, 32, 32) fp32: the whole convolutional trunk in one launch."""
+    lib = _lib.load()
+    n = images.shape[0]
+    out = torch.empty((n, cout, 32, 32), device=images.device, dtype=torch.float32)
+    _lib.check(PROFILE.run("enc_trunk", 1, lib.mmf_enc_trunk, n, cout, _lib.ptr(images), _lib.ptr(weights),
+                           _lib.ptr(scratch), _lib.ptr(out), _lib.stream_of(images)))
+    return out
 
 
 def pf_init(mean, covariance, eps_MNsd):

@@ -580,6 +580,12 @@ def test_encoder_conv_layers_match_torch(n):
         out = torch.empty(n, 8, 32, 32, device=DEV)
         ops.enc_conv3x3(n, 16, 8, mz, ops.enc_pack_conv3x3(c4), relu=False, out_nchw=out)
         assert_close(out.cpu(), c4(z_ref).cpu(), tol, msg="conv 16->8 (NCHW output)")
+        # the fused trunk (one launch, maps in L2-resident scratch) computes the same thing
+        w = ops.enc_pack_trunk([c1, c2a, c2b, c3, c4])
+        scratch = ops.enc_trunk_scratch(DEV)
+        fused_out = ops.enc_trunk(img, w, scratch, 8)
+        assert_close(fused_out.cpu(), c4(z_ref).cpu(), tol, msg="fused trunk")
+        assert torch.equal(fused_out, ops.enc_trunk(img, w, scratch, 8)), "fused trunk is not deterministic / scratch reuse"
         # the zero guards and the pad columns of every map are still zero (the next layer's padding depends on it)
         for m, ch in ((mx, 32), (mt, 32), (my, 32), (mz, 16)):
             t = m.view(n, ch // 8, 2, 1280, 16)
@@ -588,7 +594,7 @@ def test_encoder_conv_layers_match_torch(n):
             assert int(pads.count_nonzero()) == 0
 
 
-@pytest.mark.parametrize("batch", [3, 4096 + 5])
+@pytest.mark.parametrize("batch", [3, 16384 + 5])
 def test_image_encoder_module_fused_trunk_matches_torch_path(batch):
     from multimodalfilter_b200.encoders import ImageEncoder
     filt = fill_parameters(M.PushCrossmodalParticleFilter(), seed=3).to(DEV).eval()
@@ -607,7 +613,7 @@ def test_image_encoder_module_fused_trunk_matches_torch_path(batch):
             torch_out = enc(x)
         finally:
             del enc.fused_trunk
-    assert launched >= 5, "the fused trunk did not run"
+    assert launched >= 1, "the fused trunk did not run"
     assert_close(fused_out.cpu(), torch_out.cpu(), 5e-5, msg="encoder features")
     # with autograd on the module is the plain torch Sequential (training path untouched)
     y = enc(x[:2])

@@ -74,3 +74,20 @@ if len(sys.argv) > 2:
     with torch.no_grad():
         seq(img[:, None]); torch.cuda.synchronize(); e0.record(); seq(img[:, None]); e1.record(); torch.cuda.synchronize()
     print(f"cuDNN fp32 same layers (no residual add): {e0.elapsed_time(e1):.2f} ms")
+
+# fused trunk
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 300
+img = torch.rand(n, 32, 32, device=dev) * 2 - 1
+with torch.no_grad():
+    ref = c4(F.relu(c3(F.relu(c2b(F.relu(c2a(F.relu(c1(img[:, None]))))) + F.relu(c1(img[:, None]))))))
+w = ops.enc_pack_trunk([c1, c2a, c2b, c3, c4]); sc = ops.enc_trunk_scratch(dev)
+out = ops.enc_trunk(img, w, sc, 8); torch.cuda.synchronize()
+print("fused trunk rel err", rel(out, ref), "n", n)
+out2 = ops.enc_trunk(img, w, sc, 8); torch.cuda.synchronize()
+print("second run identical", bool(torch.equal(out, out2)))
+if len(sys.argv) > 2:
+    n = int(sys.argv[2]); img = torch.rand(n, 32, 32, device=dev) * 2 - 1
+    ops.enc_trunk(img, w, sc, 8); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.enc_trunk(img, w, sc, 8); ops.enc_trunk(img, w, sc, 8); e1.record(); torch.cuda.synchronize()
+    print(f"fused trunk, {n} images: {e0.elapsed_time(e1)/2:.2f} ms")
