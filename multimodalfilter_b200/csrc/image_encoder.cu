@@ -625,6 +625,272 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
   }
 }
 
+// ---- fused trunk, A operand through TMEM ------------------------------------------------------------------------
+// The SS-form MMAs above are bound by the tensor core's shared-memory operand read (~64 B/cycle/SM measured: 164
+// cycles per K step for 8 KB of A).  Ordinary LDS moves twice that, so here the two worker groups (128 threads each,
+// thread = position row = TMEM lane) read the shifted window rows themselves and park them in TMEM with tcgen05.st;
+// the MMAs become TS-form (A from TMEM, only the small weight operand from shared memory).  A group owns a tile end to
+// end: for each of the 9 taps gather -> publish (mbarrier) -> its issuer warp fires that tap's MMAs while the group
+// gathers the next tap into the next slot of a 3-deep TMEM ring; then epilogue.  The two groups alternate tiles.
+constexpr int TS_A_SLOTS = 2;       // ring of operand batches
+constexpr int TS_BATCH = 3;         // taps per batch (one row of the 3x3 stencil): one publish / wait::st per batch
+constexpr int TS_GROUP_COLS = 256;   // TMEM per group: D 64 columns + 2 batches x 3 taps x 32 columns (hi 16 | lo 16)
+
+template <int CIN>
+__device__ __forceinline__ void gather_tap(const uint8_t* stage, int shift_row, uint32_t t_slot) {
+  // stage: planes [chunk][hi|lo][ENC_WIN_POS][16 B]; this thread's row of the shifted window
+#pragma unroll
+  for (int ks = 0; ks < CIN / 16; ++ks) {
+    const uint8_t* base = stage + (size_t)((2 * ks) * 2) * ENC_WIN_B + (size_t)shift_row * 16;
+    const uint4 h0 = *reinterpret_cast<const uint4*>(base);
+    const uint4 l0 = *reinterpret_cast<const uint4*>(base + ENC_WIN_B);
+    const uint4 h1 = *reinterpret_cast<const uint4*>(base + 2 * ENC_WIN_B);
+    const uint4 l1 = *reinterpret_cast<const uint4*>(base + 3 * ENC_WIN_B);
+    const uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+    tmem_st8(t_slot + ks * 8, hi);
+    tmem_st8(t_slot + 16 + ks * 8, lo);
+  }
+}
+
+template <int CIN, int NPAD>
+__device__ __forceinline__ void issue_tap_ts(uint32_t d, uint32_t a_slot, uint32_t w_addr, int tap, uint32_t acc) {
+  constexpr int KC = CIN / 8;
+  constexpr uint32_t IDESC2 = make_idesc(2 * NPAD, 128);
+  constexpr uint32_t IDESC1 = make_idesc(NPAD, 128);
+#pragma unroll
+  for (int ks = 0; ks < CIN / 16; ++ks) {
+    const uint32_t b = w_addr + (uint32_t)((tap * KC + 2 * ks) * 2 * NPAD) * 16;
+    const uint64_t db = make_desc_interleave(b, 2 * NPAD * 16, 128);
+    mma_ts(d, a_slot + ks * 8, db, IDESC2, (ks > 0) ? 1u : acc);
+    mma_ts(d, a_slot + 16 + ks * 8, db, IDESC1, 1);
+  }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_ts(const __grid_constant__ TrunkParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* w_s = smem;
+  uint8_t* stage0 = smem + ((TR_W_B + 127) & ~127);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + ENC_STAGES * TR_STAGE_B);
+  uint64_t* full = bars;                                  // [stage]   TMA bytes landed
+  uint64_t* stage_free = bars + ENC_STAGES;               // [stage]   the owning group has read the window (4 warps)
+  uint64_t* a_ready = bars + 2 * ENC_STAGES;              // [group][slot] tap operand in TMEM (4 warps)
+  uint64_t* a_free = a_ready + 2 * TS_A_SLOTS;            // [group][slot] the MMAs that read the slot are done
+  uint64_t* mma_done = a_free + 2 * TS_A_SLOTS;           // [group]
+  uint64_t* wbar = mma_done + 2;
+  uint64_t* tile_done = wbar + 1;                         // [layer 0..3][tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 4 * ENC_TILES);
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (tid == 0) {
+    for (int s = 0; s < ENC_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(stage_free + s, 4);
+    }
+    for (int i = 0; i < 2 * TS_A_SLOTS; ++i) {
+      mbar_init(a_ready + i, 4);
+      mbar_init(a_free + i, 1);
+    }
+    mbar_init(mma_done, 1);
+    mbar_init(mma_done + 1, 1);
+    for (int i = 0; i < 4 * ENC_TILES; ++i) mbar_init(tile_done + i, 4);
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const size_t map32 = enc_map_bytes(32);
+  uint8_t* sx = P.scratch + (size_t)blockIdx.x * 3 * map32;
+  uint8_t* st = sx + map32;
+  uint8_t* sy = st + map32;
+  constexpr int OFF_W[5] = {2 * TR_W2_B + TR_W3_B + TR_W4_B, 0, TR_W2_B, 2 * TR_W2_B, 2 * TR_W2_B + TR_W3_B};
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (elect_one_sync()) {
+      mbar_expect_tx(wbar, TR_W_B);
+      for (uint32_t off = 0; off < (uint32_t)TR_W_B; off += 32768) {
+        const uint32_t n = (uint32_t)TR_W_B - off < 32768 ? (uint32_t)TR_W_B - off : 32768;
+        bulk_g2s(w_s + off, P.weights + off, n, wbar);
+      }
+      long long c = 0;
+      int k = 0;
+      for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x, ++k) {
+        const uint32_t ipar = (uint32_t)(k & 1);
+        for (int layer = 1; layer <= 4; ++layer) {
+          const uint8_t* in = layer == 1 ? sx : layer == 2 ? st : layer == 3 ? sy : sx;
+          const int planes = layer == 4 ? 4 : 8;
+          for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
+            const int s = (int)(c % ENC_STAGES);
+            const uint32_t par = (uint32_t)((c / ENC_STAGES) & 1);
+            mbar_wait(stage_free + s, par ^ 1u);
+            uint64_t* dep = tile_done + (layer - 1) * ENC_TILES;
+            if (tile > 0) mbar_wait(dep + tile - 1, ipar);
+            mbar_wait(dep + tile, ipar);
+            if (tile + 1 < ENC_TILES) mbar_wait(dep + tile + 1, ipar);
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            const uint8_t* src = in + (size_t)(ENC_GUARD + tile * 128 - ENC_HALO) * 16;
+            mbar_expect_tx(full + s, (uint32_t)planes * ENC_WIN_B);
+            for (int pl = 0; pl < planes; ++pl)
+              bulk_g2s(stage0 + s * TR_STAGE_B + pl * ENC_WIN_B, src + (size_t)pl * ENC_PLANE_B, ENC_WIN_B, full + s);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 2) {
+    // ----------------------------------------------------------------- MMA issuer of worker group (warp - 1)
+    const int e = warp - 1;
+    mbar_wait(wbar, 0);
+    if (elect_one_sync()) {
+      const uint32_t w_addr = smem_u32(w_s);
+      const uint32_t gbase = tmem_base + e * TS_GROUP_COLS;
+      long long c = 0, taps = 0, mine = 0;
+      for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
+        for (int layer = 1; layer <= 4; ++layer) {
+          for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
+            if ((int)(c & 1) != e) continue;
+            for (int batch = 0; batch < 9 / TS_BATCH; ++batch, ++taps) {
+              const int slot = (int)(taps % TS_A_SLOTS);
+              const uint32_t par = (uint32_t)((taps / TS_A_SLOTS) & 1);
+              mbar_wait(a_ready + e * TS_A_SLOTS + slot, par);
+              tc_fence_after();
+#pragma unroll
+              for (int i = 0; i < TS_BATCH; ++i) {
+                const int tap = batch * TS_BATCH + i;
+                const uint32_t a_slot = gbase + 64 + (slot * TS_BATCH + i) * 32;
+                const uint32_t acc = tap > 0 ? 1u : 0u;
+                if (layer <= 2) issue_tap_ts<32, 32>(gbase, a_slot, w_addr + OFF_W[layer], tap, acc);
+                else if (layer == 3) issue_tap_ts<32, 16>(gbase, a_slot, w_addr + OFF_W[3], tap, acc);
+                else issue_tap_ts<16, 16>(gbase, a_slot, w_addr + OFF_W[4], tap, acc);
+              }
+              tc_commit(a_free + e * TS_A_SLOTS + slot);
+            }
+            tc_commit(mma_done + e);
+            ++mine;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------- worker groups: stem, tap gathers, epilogues
+    const int e = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + (tid & 31);
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t gbase = tmem_base + e * TS_GROUP_COLS + lane_off;
+    mbar_wait(wbar, 0);
+    const float* wstem = reinterpret_cast<const float*>(w_s + OFF_W[0]);
+    long long g = 0, c = 0, taps = 0, mine = 0;
+    for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
+      const float* im = P.images + (size_t)image * 1024;
+      for (int layer = 0; layer < TR_LAYERS; ++layer) {
+        for (int tile = 0; tile < ENC_TILES; ++tile, ++g) {
+          const long long cc = c;
+          if (layer > 0) ++c;
+          // stem tiles alternate by the global item index, convolution tiles by the convolution counter (the
+          // issuer warps use the same rule)
+          if (layer == 0 ? ((int)(g & 1) != e) : ((int)(cc & 1) != e)) continue;
+          const int pos = tile * 128 + r;
+          const bool valid = enc_valid(pos);
+          if (layer == 0) {
+            float acc[32];
+#pragma unroll
+            for (int ch = 0; ch < 32; ++ch) acc[ch] = wstem[25 * 32 + ch];
+            if (valid) {
+              const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
+              for (int ky = 0; ky < 5; ++ky) {
+                const int yy = y + ky - 2;
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                  const int xx = x + kx - 2;
+                  const float p = (yy >= 0 && yy < 32 && xx >= 0 && xx < 32) ? __ldg(im + yy * 32 + xx) : 0.0f;
+                  const float4* w4 = reinterpret_cast<const float4*>(wstem + (ky * 5 + kx) * 32);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 t = w4[q];
+                    acc[4 * q] = fmaf(t.x, p, acc[4 * q]);
+                    acc[4 * q + 1] = fmaf(t.y, p, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(t.z, p, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(t.w, p, acc[4 * q + 3]);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = valid ? fmaxf(acc[kc * 8 + j], 0.0f) : 0.0f;
+              uint4 hi4, lo4;
+              split8(v, hi4, lo4);
+              uint8_t* plane = sx + (size_t)(kc * 2) * ENC_PLANE_B + (size_t)(ENC_GUARD + pos) * 16;
+              *reinterpret_cast<uint4*>(plane) = hi4;
+              *reinterpret_cast<uint4*>(plane + ENC_PLANE_B) = lo4;
+            }
+            publish_tile(tile_done + tile);
+            continue;
+          }
+          // ---- gather the 9 shifted windows into the TMEM ring ----
+          const int s = (int)(cc % ENC_STAGES);
+          const uint32_t spar = (uint32_t)((cc / ENC_STAGES) & 1);
+          mbar_wait(full + s, spar);
+          const uint8_t* stage = stage0 + s * TR_STAGE_B;
+          for (int batch = 0; batch < 9 / TS_BATCH; ++batch, ++taps) {
+            const int slot = (int)(taps % TS_A_SLOTS);
+            const uint32_t par = (uint32_t)((taps / TS_A_SLOTS) & 1);
+            mbar_wait(a_free + e * TS_A_SLOTS + slot, par ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < TS_BATCH; ++i) {
+              const int tap = batch * TS_BATCH + i;
+              const int shift_row = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1) + r;
+              const uint32_t t_slot = gbase + 64 + (slot * TS_BATCH + i) * 32;
+              if (layer <= 3) gather_tap<32>(stage, shift_row, t_slot);
+              else gather_tap<16>(stage, shift_row, t_slot);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(a_ready + e * TS_A_SLOTS + slot);
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(stage_free + s);  // this warp is done reading the window
+          // ---- epilogue ----
+          mbar_wait(mma_done + e, (uint32_t)(mine & 1));
+          ++mine;
+          tc_fence_after();
+          uint32_t d[32];
+          if (layer <= 2) load_accumulator<32>(gbase, d);
+          else load_accumulator<16>(gbase, reinterpret_cast<uint32_t(&)[16]>(d[0]));
+          tc_fence_before();
+          const float* bias_s = reinterpret_cast<const float*>(
+              w_s + OFF_W[layer] + (layer <= 2 ? TR_W2_B - 128 : layer == 3 ? TR_W3_B - 64 : TR_W4_B - 64));
+          if (layer == 1) epilogue_conv<32>(d, bias_s, nullptr, true, valid, pos, st, nullptr, 0);
+          else if (layer == 2) epilogue_conv<32>(d, bias_s, sx, true, valid, pos, sy, nullptr, 0);
+          else if (layer == 3) epilogue_conv<16>(d, bias_s, nullptr, true, valid, pos, sx, nullptr, 0);
+          else epilogue_conv<16>(d, bias_s, nullptr, false, valid, pos, nullptr, P.out_nchw + (size_t)image * P.cout * 1024, P.cout);
+          if (layer < 4) publish_tile(tile_done + layer * ENC_TILES + tile);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 static int trunk_grid(int* grid_out) {
   int dev = 0, sms = 148;
   MMF_CUDA(cudaGetDevice(&dev));
@@ -661,11 +927,19 @@ int launch_enc_trunk(int n_images, int cout, const float* images, const void* we
   if (configured_dev != dev) {
     rc = opt_in_shared_memory(k_enc_trunk, &window);
     if (rc) return rc;
+    rc = opt_in_shared_memory(k_enc_trunk_ts, &window);
+    if (rc) return rc;
     configured_dev = dev;
   }
   MMF_REQUIRE(smem <= window, "encoder trunk needs %zu B of shared memory (window %zu B)", smem, window);
   if (grid > n_images) grid = n_images;
-  k_enc_trunk<<<grid, ENC_THREADS, smem, stream>>>(P);
+  // MMF_ENC_VARIANT: 0 = A operand read from shared memory by the MMAs (SS form, default: 5.25 ms per 16,384 images),
+  //                  1 = A through TMEM (TS form; parity-green but 7.0 ms: the gather -> publish -> MMA -> epilogue chain
+  //                      of only two tile groups leaves every unit < 35 % busy)
+  int variant = 0;
+  if (const char* env = getenv("MMF_ENC_VARIANT")) variant = atoi(env);
+  if (variant == 1) k_enc_trunk_ts<<<grid, ENC_THREADS, smem, stream>>>(P);
+  else k_enc_trunk<<<grid, ENC_THREADS, smem, stream>>>(P);
   MMF_LAUNCH_CHECK("k_enc_trunk");
   return MMF_OK;
 }
