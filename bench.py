@@ -43,6 +43,8 @@ WORKLOADS = {
     "c4": ("PushCrossmodalParticleFilter", 2, 8192, 30, 15,
            "Push crossmodal PF BPTT training step (fwd+bwd, subsequence 16, 8192 trajectories), gradient allreduce"),
 }
+# bounded CPU sample (trajectories, steps) of the big workloads: a few seconds of host work per timed run
+CPU_SAMPLE = {"c3": (64, 20), "c4": (256, 15)}
 FLOP_PER_PARTICLE_STEP = {2: 189_824.0, 3: 190_336.0}  # BASELINE.md section 4 (hoisted minimum)
 
 
@@ -53,6 +55,20 @@ def measured_peaks():
             d = json.load(f)
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+def ncu_traffic(capture):
+    """dram read + write bytes per launch of a kernel from the committed ncu --set full capture
+    (profiles/r01_ncu_metrics.json, written by tools/gpu_round.sh + the extraction step), or None."""
+    path = os.path.join(REPO, "profiles", "r01_ncu_metrics.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f).get(capture)
+    if not d or "dram_read" not in d or "dram_write" not in d:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return sum(d[k]["value"] * scale.get(d[k]["unit"], 1.0) for k in ("dram_read", "dram_write"))
 
 
 class ClockSampler:
@@ -107,7 +123,7 @@ def build_inputs(workload, seed=0):
     return states, obs, controls
 
 
-def run_cpu_oracle(workload, n_sample, t_sample, repeats=1):
+def run_cpu_oracle(workload, n_sample, t_sample, repeats=1, warm=True):
     """The reference's CPU path (oracle port: eager PyTorch on the host cores) on a bounded sample of
     the workload.  Returns (particle-steps/s, description)."""
     from multimodalfilter_b200.synthetic import fill_parameters, synthetic_trajectories
@@ -121,6 +137,11 @@ def run_cpu_oracle(workload, n_sample, t_sample, repeats=1):
     states, obs, controls = synthetic_trajectories(t_sample + 1, n_sample, sd, seed=0)
     cov = (torch.eye(sd) * 0.1)[None].expand(n_sample, sd, sd)
     best = None
+    if warm:  # first call pays for thread-pool start-up, allocator growth and oneDNN primitive creation: not timed
+        with torch.no_grad():
+            nw = min(n_sample, 4)
+            filt.initialize_beliefs(mean=states[0][:nw], covariance=cov[:nw])
+            filt.forward_loop(observations={k: v[1:3, :nw] for k, v in obs.items()}, controls=controls[1:3, :nw])
     for _ in range(repeats):
         torch.manual_seed(0)
         t0 = time.perf_counter()
@@ -139,7 +160,7 @@ def reference_arm(args):
     if rank != 0:
         return
     name, sd, N, M, T, cfg = WORKLOADS[args.workload]
-    n_s, t_s = (8, 4) if args.workload == "c3" else (min(N, 32), min(T, 50))
+    n_s, t_s = CPU_SAMPLE.get(args.workload, (min(N, 32), min(T, 50)))
     torch.set_num_threads(os.cpu_count() or 1)
     times = []
     for i in range(args.warmup + args.steps):
@@ -423,7 +444,8 @@ def main():
             line["roofline"] = {
                 "kernel": "k_particle_chain (mmf_pf_predict_measure)", "bound": "tensor", "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained", "avg_launch_ms": k["avg_ms"],
+                "traffic": ncu_traffic("prof_chain_tc") if args.workload == "c3" else None, "traffic_unit": "dram bytes per launch (ncu --set full, C3 step)",
+                "peak_source": f"{peaks['source']} bf16 sustained", "avg_launch_ms": k["avg_ms"],
                 "share_of_step": k["total_ms"] / (ms_resident * args.steps),
                 "other_kernels": {n: {"avg_ms": v["avg_ms"], "share": v["total_ms"] / (ms_resident * args.steps)}
                                   for n, v in prof["kernels"].items() if n != "pf_predict_measure"},
@@ -445,7 +467,7 @@ def main():
                                 "note": "latency/parallelism-bound by construction at N=256 (SURVEY.md section 7.6)"}
         if not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            n_s, t_s = (8, 4) if args.workload == "c3" else (min(N, 32), min(T, 50))
+            n_s, t_s = CPU_SAMPLE.get(args.workload, (min(N, 32), min(T, 50)))
             rate, sample, dt = run_cpu_oracle(args.workload, n_s, t_s)
             line["cpu_baseline"] = {"value": rate, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "sample": sample, "seconds": dt}
