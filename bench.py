@@ -42,6 +42,8 @@ WORKLOADS = {
            "Door task crossmodal EKF eval (state_dim=3), 256 trajectories x 100 steps"),
     "c4": ("PushCrossmodalParticleFilter", 2, 8192, 30, 15,
            "Push crossmodal PF BPTT training step (fwd+bwd, subsequence 16, 8192 trajectories), gradient allreduce"),
+    "c5": ("PushUnimodalParticleFilter", 2, 16384, 0, 2,
+           "Particle-count sweep 1K-1M particles x 16K trajectories, trajectory-sharded"),
 }
 # bounded CPU sample (trajectories, steps) of the big workloads: a few seconds of host work per timed run
 CPU_SAMPLE = {"c3": (64, 20), "c4": (256, 15)}
@@ -282,6 +284,88 @@ def bptt_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def sweep_arm(args):
+    """BASELINE config C5: particle-count sweep M = 1K ... 1M at 16K trajectories (sharded over the ranks).
+    16K x 1M particles do not fit one GPU (196 GB of state), so the trajectories are TILED (tile-of-trajectories outer,
+    time inner: legal because trajectories are independent); a "step" here times a bounded number of tiles per M
+    (up to 2 tiles x 2 filter steps, a tile holds up to 134 M particles) and reports particle-steps/s per M -- tiles are independent
+    and identical, so the rate of the full 16K-trajectory sweep point is the same number.  value = geometric mean."""
+    import torch.distributed as dist
+
+    from multimodalfilter_b200 import _lib
+    from multimodalfilter_b200.crossmodal import models as M_
+    from multimodalfilter_b200.synthetic import fill_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().mmf_device_check())
+    name, sd, N_total, _, T, cfg = WORKLOADS["c5"]
+    n_rank = N_total // world
+    filt = fill_parameters(M_.MODEL_TYPES["push"][name](), seed=0).to(dev).eval()
+    filt.precision = args.precision or "bf16x3"
+    filt.resample_mode = args.resample_mode
+    plan = filt.fused_plan()
+    g = torch.Generator(device=dev).manual_seed(rank)
+    points = []
+    for Mp in (1024, 4096, 16384, 65536, 262144, 1048576):
+        n_tile = max(1, min(n_rank, (1 << 27) // Mp))
+        tiles = min(2, max(1, n_rank // n_tile))
+        filt.num_particles = Mp
+        mean = torch.randn(n_tile, sd, device=dev, generator=g)
+        cov = (torch.eye(sd, device=dev) * 0.1)[None].expand(n_tile, sd, sd).contiguous()
+        feats = [torch.randn(T, n_tile, 64, device=dev, generator=g), torch.randn(T, n_tile, 128, device=dev, generator=g)]
+        controls = torch.randn(T, n_tile, 7, device=dev, generator=g)
+
+        def one_pass():
+            with torch.no_grad():
+                for _ in range(tiles):
+                    filt.initialize_beliefs(mean=mean, covariance=cov)
+                    for t in range(T):
+                        filt.forward(observations=None, controls=controls[t], _hoisted=([f[t] for f in feats], None))
+
+        for _ in range(max(1, args.warmup)):
+            one_pass()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            one_pass()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        rate = world * tiles * n_tile * Mp * T / (float(ms) / 1e3)
+        points.append({"particles": Mp, "trajectories_per_tile": n_tile, "tiles_timed": tiles, "ms": float(ms),
+                       "particle_steps_per_s": rate})
+        del mean, cov, feats, controls
+        filt.particle_states = filt.particle_log_weights = None
+        torch.cuda.empty_cache()
+    if rank == 0:
+        import math
+        value = math.exp(sum(math.log(p["particle_steps_per_s"]) for p in points) / len(points))
+        print(json.dumps({
+            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(p["ms"] for p in points),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": filt.precision,
+            "data": "synthetic",
+            "config": {"workload": cfg, "id": "c5", "model": name, "trajectories_total": N_total,
+                       "filter_steps_per_tile": T, "resample": args.resample_mode,
+                       "note": "value = geometric mean over the sweep; bounded tiles per point, see sweep"},
+            "sweep": points,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -299,6 +383,8 @@ def main():
         return reference_arm(args)
     if args.workload == "c4":
         return bptt_arm(args)
+    if args.workload == "c5":
+        return sweep_arm(args)
 
     import torch.distributed as dist
 
