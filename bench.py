@@ -439,10 +439,7 @@ def main():
         def resident_pass():
             with torch.no_grad():
                 filt.initialize_beliefs(mean=dev_mean0, covariance=cov)
-                est = None
-                for t in range(T):
-                    hoisted = ([None if f is None else f[t] for f in feats], None if modw is None else modw[t])
-                    est = filt.forward(observations=None, controls=dev_controls[t], _hoisted=hoisted)
+                est = filt.forward_loop_hoisted(feats, modw, dev_controls)  # graph replay when the problem is small
             return est
     else:
         filters = list(filt.filter_models)
@@ -500,7 +497,8 @@ def main():
     # inputs per pass (>= 100 MB of particle state + features) exceed nothing like L2 reuse across passes:
     # every step rewrites the N*M particle set (C3: 49 MB states+weights per step, new noise each step).
     ms_resident, clocks, prof = timed(resident_pass, args.steps, args.warmup, profile=True)
-    ms_e2e, clocks_e2e, _ = timed(e2e_pass, max(1, min(args.steps, 3)), 1)
+    # small workloads capture their CUDA graph on the second call: keep that out of the timed region
+    ms_e2e, clocks_e2e, _ = timed(e2e_pass, max(1, min(args.steps, 3)), 1 if args.workload == "c3" else 3)
 
     value = world * units_per_pass / (ms_resident / 1e3)
     e2e_value = world * units_per_pass / (ms_e2e / 1e3)

@@ -78,6 +78,9 @@ class ParticleFilter(Filter):
         self.resample_mode = "multinomial"
         self.precision = "bf16x3"
         self.debug = None  # set to a dict to capture intermediates of the last fused step
+        # forward_loop on small problems is launch-bound (~15 launches + Python per step): the second call with the
+        # same shapes captures the whole T-step recursion in a CUDA graph and later calls replay it
+        self.graph_max_particles = 1 << 16  # N * M up to which forward_loop is graph-captured; 0 disables
 
     # ---- plan management -------------------------------------------------------------------------
     def fused_plan(self):
@@ -273,11 +276,94 @@ class ParticleFilter(Filter):
         feats, modw = self.hoist_observations(plan, observations, T, N)
         if isinstance(observations, fused.StagedObservations):
             observations.ready(T * N)
+        return self.forward_loop_hoisted(feats, modw, controls)
+
+    def forward_loop_hoisted(self, feats, modw, controls) -> torch.Tensor:
+        """The recursion proper, given the per-head observation features (T, N, F_k) and modality log-weights
+        (T, N, K) of ``hoist_observations``: CUDA-graph replay for small problems, one kernel sequence per step
+        otherwise."""
+        T, N = controls.shape[:2]
+        replayed = self._forward_loop_graph(feats, modw, controls, T, N)
+        if replayed is not None:
+            return replayed
         estimates = controls.new_zeros((T, N, self.state_dim), dtype=torch.float32)
         for t in range(T):
             hoisted = ([None if f is None else f[t] for f in feats], None if modw is None else modw[t])
             estimates[t] = self.forward(observations=None, controls=controls[t], _hoisted=hoisted)
         return estimates
+
+    def _forward_loop_graph(self, feats, modw, controls, T, N):
+        """CUDA-graph replay of the hoisted T-step recursion.  Returns the estimates,
+        or None when the loop has to run eagerly (large problem, injected noise, debug capture, first sight of a
+        configuration, or a capture that failed once)."""
+        M_in = self.particle_states.shape[1]
+        if (
+            not self.graph_max_particles
+            or N * max(M_in, self.num_particles) > self.graph_max_particles
+            or self.noise is not None
+            or self.debug is not None
+            or controls.dtype != torch.float32
+        ):
+            return None
+        resample, mode = self._modes()
+        if not resample and self.num_particles != M_in:
+            return None
+        key = (
+            T, N, M_in, self.num_particles, self.state_dim, str(controls.device), tuple(controls.shape), mode,
+            self.estimation_method, float(self.soft_resample_alpha), self.precision,
+            tuple(None if f is None else tuple(f.shape) for f in feats), None if modw is None else tuple(modw.shape),
+            tuple(self.fused_plan().enabled()), tuple((p.data_ptr(), p._version) for p in self.parameters()),
+        )
+        cache = self.__dict__.setdefault("_mmf_loop_graph", {"key": None, "graph": None, "static": None})
+        if cache["key"] != key:
+            cache.update(key=key, graph=None, static=None)  # first sight: run eagerly (also warms every launcher)
+            return None
+        if cache["graph"] is False:
+            return None
+        if cache["graph"] is None:
+            st = {
+                "feats": [None if f is None else f.clone() for f in feats],
+                "modw": None if modw is None else modw.clone(),
+                "controls": controls.clone(),
+                "states0": self.particle_states.detach().clone(),
+                "logw0": self.particle_log_weights.detach().clone(),
+                "est": controls.new_zeros((T, N, self.state_dim), dtype=torch.float32),
+            }
+            live = (self.particle_states, self.particle_log_weights)
+            graph = torch.cuda.CUDAGraph()
+            launches_before = ops.PROFILE.launches
+            try:
+                self.particle_states, self.particle_log_weights = st["states0"], st["logw0"]
+                with torch.cuda.graph(graph):
+                    for t in range(T):
+                        hoisted = ([None if f is None else f[t] for f in st["feats"]],
+                                   None if st["modw"] is None else st["modw"][t])
+                        st["est"][t] = self.forward(observations=None, controls=st["controls"][t], _hoisted=hoisted)
+                st["statesT"], st["logwT"] = self.particle_states, self.particle_log_weights
+                # kernels recorded into the graph: they run at every replay, not during capture
+                st["launches"] = ops.PROFILE.launches - launches_before
+                ops.PROFILE.launches = launches_before
+            except Exception:  # capture is an optimisation: never let it take the eager path down with it
+                self.particle_states, self.particle_log_weights = live
+                cache.update(graph=False, static=None)
+                torch.cuda.synchronize()
+                return None
+            self.particle_states, self.particle_log_weights = live
+            cache.update(graph=graph, static=st)
+        st = cache["static"]
+        for dst, src in zip(st["feats"], feats):
+            if dst is not None:
+                dst.copy_(src)
+        if st["modw"] is not None:
+            st["modw"].copy_(modw)
+        st["controls"].copy_(controls)
+        st["states0"].copy_(self.particle_states)
+        st["logw0"].copy_(self.particle_log_weights)
+        cache["graph"].replay()
+        ops.PROFILE.launches += st["launches"]
+        self.particle_states = st["statesT"].clone()
+        self.particle_log_weights = st["logwT"].clone()
+        return st["est"].clone()
 
     def hoist_observations(self, plan, observations, T, N):
         """The observation encoders and the weight model do not depend on the particles: run them
