@@ -626,58 +626,127 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
 }
 
 // ---- fused trunk, A operand through TMEM ------------------------------------------------------------------------
-// The SS-form MMAs above are bound by the tensor core's shared-memory operand read (~64 B/cycle/SM measured: 164
-// cycles per K step for 8 KB of A).  Ordinary LDS moves twice that, so here the two worker groups (128 threads each,
-// thread = position row = TMEM lane) read the shifted window rows themselves and park them in TMEM with tcgen05.st;
-// the MMAs become TS-form (A from TMEM, only the small weight operand from shared memory).  A group owns a tile end to
-// end: for each of the 9 taps gather -> publish (mbarrier) -> its issuer warp fires that tap's MMAs while the group
-// gathers the next tap into the next slot of a 3-deep TMEM ring; then epilogue.  The two groups alternate tiles.
-constexpr int TS_A_SLOTS = 2;       // ring of operand batches
-constexpr int TS_BATCH = 3;         // taps per batch (one row of the 3x3 stencil): one publish / wait::st per batch
-constexpr int TS_GROUP_COLS = 256;   // TMEM per group: D 64 columns + 2 batches x 3 taps x 32 columns (hi 16 | lo 16)
+// The SS-form MMAs above are bound by the tensor core's shared-memory operand read (~64-75 B/cycle/SM measured: 164
+// cycles per K step for 8 KB of A).  Ordinary LDS moves twice that, so here dedicated GATHER warps (two groups of 128
+// threads, thread = position row = TMEM lane) read the shifted window rows themselves and park them in TMEM with
+// tcgen05.st; the MMAs become TS-form (A from TMEM, only the small weight operand from shared memory).  Roles:
+//   warp 0        TMA producer (window ring in shared memory, as above)
+//   warps 1, 2    MMA issuers, one per gather group
+//   warps 4-11    gather groups 0/1: tiles alternate between them; per tile 9 taps in batches of TS_BATCH taps,
+//                 a ring of TS_A_SLOTS batches per group in TMEM (a_ready / a_free mbarriers)
+//   warps 12-19   epilogue groups 0/1 (and the stem): four accumulator slots of 64 columns (mma_done / tmem_free)
+// so a gather group starts its next tile while the previous one is still in the tensor pipe / epilogue.
+constexpr int TS_A_SLOTS = 2;        // ring of operand batches per gather group
+constexpr int TS_BATCH = 2;          // taps per batch: one wait::st + publish per batch
+constexpr int TS_BATCHES = (9 + TS_BATCH - 1) / TS_BATCH;
+constexpr int TS_D_SLOTS = 4;        // accumulator slots (64 columns each): columns [0, 256)
+constexpr int TS_A_BASE = 256;       // gather group e owns columns [256 + 128 e, 256 + 128 e + 128): 4 tap slots of 32
+constexpr int TS_THREADS = 640;
 
-template <int CIN>
+// LO_SS: the lo halves stay in shared memory and are read by SS-form MMAs (splits the operand feed between the LSU
+// path, ~128 B/cycle, and the tensor core's own shared-memory read, ~64 B/cycle)
+template <int CIN, bool LO_SS>
 __device__ __forceinline__ void gather_tap(const uint8_t* stage, int shift_row, uint32_t t_slot) {
   // stage: planes [chunk][hi|lo][ENC_WIN_POS][16 B]; this thread's row of the shifted window
 #pragma unroll
   for (int ks = 0; ks < CIN / 16; ++ks) {
     const uint8_t* base = stage + (size_t)((2 * ks) * 2) * ENC_WIN_B + (size_t)shift_row * 16;
     const uint4 h0 = *reinterpret_cast<const uint4*>(base);
-    const uint4 l0 = *reinterpret_cast<const uint4*>(base + ENC_WIN_B);
     const uint4 h1 = *reinterpret_cast<const uint4*>(base + 2 * ENC_WIN_B);
-    const uint4 l1 = *reinterpret_cast<const uint4*>(base + 3 * ENC_WIN_B);
     const uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    const uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
     tmem_st8(t_slot + ks * 8, hi);
-    tmem_st8(t_slot + 16 + ks * 8, lo);
+    if (!LO_SS) {
+      const uint4 l0 = *reinterpret_cast<const uint4*>(base + ENC_WIN_B);
+      const uint4 l1 = *reinterpret_cast<const uint4*>(base + 3 * ENC_WIN_B);
+      const uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+      tmem_st8(t_slot + 16 + ks * 8, lo);
+    }
   }
 }
 
-template <int CIN, int NPAD>
-__device__ __forceinline__ void issue_tap_ts(uint32_t d, uint32_t a_slot, uint32_t w_addr, int tap, uint32_t acc) {
+template <int CIN, int NPAD, bool LO_SS>
+__device__ __forceinline__ void issue_tap_ts(uint32_t d, uint32_t a_slot, uint32_t w_addr, uint32_t st_addr, int tap,
+                                             uint32_t acc) {
   constexpr int KC = CIN / 8;
   constexpr uint32_t IDESC2 = make_idesc(2 * NPAD, 128);
   constexpr uint32_t IDESC1 = make_idesc(NPAD, 128);
+  const int shift = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1);
 #pragma unroll
   for (int ks = 0; ks < CIN / 16; ++ks) {
     const uint32_t b = w_addr + (uint32_t)((tap * KC + 2 * ks) * 2 * NPAD) * 16;
     const uint64_t db = make_desc_interleave(b, 2 * NPAD * 16, 128);
     mma_ts(d, a_slot + ks * 8, db, IDESC2, (ks > 0) ? 1u : acc);
-    mma_ts(d, a_slot + 16 + ks * 8, db, IDESC1, 1);
+    if (LO_SS) {
+      const uint32_t a_lo = st_addr + (uint32_t)((2 * ks) * 2 + 1) * ENC_WIN_B + (uint32_t)shift * 16;
+      mma_ss(d, make_desc_interleave(a_lo, 2 * ENC_WIN_B, 128), db, IDESC1, 1);
+    } else {
+      mma_ts(d, a_slot + 16 + ks * 8, db, IDESC1, 1);
+    }
   }
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_ts(const __grid_constant__ TrunkParams P) {
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// epilogue straight from TMEM in 8-channel chunks (keeps the register footprint small: 640 threads -> 96 registers)
+template <int NPAD>
+__device__ __forceinline__ void epilogue_from_tmem(uint32_t taddr, const float* bias_s, const uint8_t* res_map, bool relu,
+                                                   bool valid, int pos, uint8_t* out_map, float* out_img, int cout) {
+  const size_t plane_off = (size_t)(ENC_GUARD + pos) * 16;
+#pragma unroll
+  for (int kc = 0; kc < NPAD / 8; ++kc) {
+    uint32_t d[8], e[8];
+    tmem_ld8(taddr + kc * 8, d);
+    tmem_ld8(taddr + NPAD + kc * 8, e);
+    tc_wait_ld();
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(d[j]) + __uint_as_float(e[j])) + bias_s[kc * 8 + j];
+    if (res_map != nullptr) {
+      const uint8_t* rp = res_map + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
+      float x[8];
+      unpack8(*reinterpret_cast<const uint4*>(rp), *reinterpret_cast<const uint4*>(rp + ENC_PLANE_B), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += x[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (relu) v[j] = fmaxf(v[j], 0.0f);
+      if (!valid) v[j] = 0.0f;
+    }
+    if (out_map != nullptr) {
+      uint4 hi4, lo4;
+      split8(v, hi4, lo4);
+      uint8_t* op = out_map + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
+      *reinterpret_cast<uint4*>(op) = hi4;
+      *reinterpret_cast<uint4*>(op + ENC_PLANE_B) = lo4;
+    }
+    if (out_img != nullptr && valid) {
+      const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (kc * 8 + j < cout) out_img[((size_t)(kc * 8 + j) * 32 + y) * 32 + x] = v[j];
+    }
+  }
+}
+
+template <bool LO_SS>
+__global__ void __launch_bounds__(TS_THREADS, 1) k_enc_trunk_ts(const __grid_constant__ TrunkParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
   uint8_t* stage0 = smem + ((TR_W_B + 127) & ~127);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + ENC_STAGES * TR_STAGE_B);
   uint64_t* full = bars;                                  // [stage]   TMA bytes landed
-  uint64_t* stage_free = bars + ENC_STAGES;               // [stage]   the owning group has read the window (4 warps)
-  uint64_t* a_ready = bars + 2 * ENC_STAGES;              // [group][slot] tap operand in TMEM (4 warps)
-  uint64_t* a_free = a_ready + 2 * TS_A_SLOTS;            // [group][slot] the MMAs that read the slot are done
-  uint64_t* mma_done = a_free + 2 * TS_A_SLOTS;           // [group]
-  uint64_t* wbar = mma_done + 2;
+  uint64_t* stage_free = bars + ENC_STAGES;               // [stage]   the gather group has read the window (4 warps)
+  uint64_t* a_ready = bars + 2 * ENC_STAGES;              // [group][slot] operand batch in TMEM (4 warps)
+  uint64_t* a_free = a_ready + 2 * TS_A_SLOTS;            // [group][slot] the MMAs that read the batch are done
+  uint64_t* mma_done = a_free + 2 * TS_A_SLOTS;           // [d slot] accumulator complete
+  uint64_t* tmem_free = mma_done + TS_D_SLOTS;            // [d slot] epilogue has read the accumulator (4 warps)
+  uint64_t* wbar = tmem_free + TS_D_SLOTS;
   uint64_t* tile_done = wbar + 1;                         // [layer 0..3][tile]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 4 * ENC_TILES);
 
@@ -686,14 +755,16 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_ts(const __grid_co
   if (tid == 0) {
     for (int s = 0; s < ENC_STAGES; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(stage_free + s, 4);
+      mbar_init(stage_free + s, LO_SS ? 5 : 4);  // 4 gather warps (+ the MMAs that read the lo planes)
     }
     for (int i = 0; i < 2 * TS_A_SLOTS; ++i) {
       mbar_init(a_ready + i, 4);
       mbar_init(a_free + i, 1);
     }
-    mbar_init(mma_done, 1);
-    mbar_init(mma_done + 1, 1);
+    for (int i = 0; i < TS_D_SLOTS; ++i) {
+      mbar_init(mma_done + i, 1);
+      mbar_init(tmem_free + i, 4);
+    }
     for (int i = 0; i < 4 * ENC_TILES; ++i) mbar_init(tile_done + i, 4);
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -748,58 +819,102 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_ts(const __grid_co
     }
     __syncwarp();
   } else if (warp == 1 || warp == 2) {
-    // ----------------------------------------------------------------- MMA issuer of worker group (warp - 1)
+    // ----------------------------------------------------------------- MMA issuer of gather group (warp - 1)
     const int e = warp - 1;
     mbar_wait(wbar, 0);
     if (elect_one_sync()) {
       const uint32_t w_addr = smem_u32(w_s);
-      const uint32_t gbase = tmem_base + e * TS_GROUP_COLS;
-      long long c = 0, taps = 0, mine = 0;
+      const uint32_t abase = tmem_base + TS_A_BASE + e * 128;
+      long long c = 0, batches = 0;
       for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
         for (int layer = 1; layer <= 4; ++layer) {
           for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
             if ((int)(c & 1) != e) continue;
-            for (int batch = 0; batch < 9 / TS_BATCH; ++batch, ++taps) {
-              const int slot = (int)(taps % TS_A_SLOTS);
-              const uint32_t par = (uint32_t)((taps / TS_A_SLOTS) & 1);
+            const int ds = (int)(c % TS_D_SLOTS);
+            const uint32_t dpar = (uint32_t)((c / TS_D_SLOTS) & 1);
+            const uint32_t d = tmem_base + ds * 64;
+            const uint32_t st_addr = smem_u32(stage0 + (int)(c % ENC_STAGES) * TR_STAGE_B);
+            mbar_wait(tmem_free + ds, dpar ^ 1u);
+            for (int batch = 0; batch < TS_BATCHES; ++batch, ++batches) {
+              const int slot = (int)(batches % TS_A_SLOTS);
+              const uint32_t par = (uint32_t)((batches / TS_A_SLOTS) & 1);
               mbar_wait(a_ready + e * TS_A_SLOTS + slot, par);
               tc_fence_after();
 #pragma unroll
               for (int i = 0; i < TS_BATCH; ++i) {
                 const int tap = batch * TS_BATCH + i;
-                const uint32_t a_slot = gbase + 64 + (slot * TS_BATCH + i) * 32;
-                const uint32_t acc = tap > 0 ? 1u : 0u;
-                if (layer <= 2) issue_tap_ts<32, 32>(gbase, a_slot, w_addr + OFF_W[layer], tap, acc);
-                else if (layer == 3) issue_tap_ts<32, 16>(gbase, a_slot, w_addr + OFF_W[3], tap, acc);
-                else issue_tap_ts<16, 16>(gbase, a_slot, w_addr + OFF_W[4], tap, acc);
+                if (tap < 9) {
+                  const uint32_t a_slot = abase + (slot * TS_BATCH + i) * 32;
+                  const uint32_t acc = tap > 0 ? 1u : 0u;
+                  if (layer <= 2) issue_tap_ts<32, 32, LO_SS>(d, a_slot, w_addr + OFF_W[layer], st_addr, tap, acc);
+                  else if (layer == 3) issue_tap_ts<32, 16, LO_SS>(d, a_slot, w_addr + OFF_W[3], st_addr, tap, acc);
+                  else issue_tap_ts<16, 16, LO_SS>(d, a_slot, w_addr + OFF_W[4], st_addr, tap, acc);
+                }
               }
               tc_commit(a_free + e * TS_A_SLOTS + slot);
             }
-            tc_commit(mma_done + e);
-            ++mine;
+            tc_commit(mma_done + ds);
+            if (LO_SS) tc_commit(stage_free + (int)(c % ENC_STAGES));
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ------------------------------------------------------- worker groups: stem, tap gathers, epilogues
+  } else if (warp >= 4 && warp < 12) {
+    // --------------------------------------------------------------------------------------- gather groups
     const int e = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + (tid & 31);
+    const uint32_t abase = tmem_base + TS_A_BASE + e * 128 + ((uint32_t)(quad * 32) << 16);
+    long long c = 0, batches = 0;
+    for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
+      for (int layer = 1; layer <= 4; ++layer) {
+        for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
+          if ((int)(c & 1) != e) continue;
+          const int s = (int)(c % ENC_STAGES);
+          const uint32_t spar = (uint32_t)((c / ENC_STAGES) & 1);
+          mbar_wait(full + s, spar);
+          const uint8_t* stage = stage0 + s * TR_STAGE_B;
+          for (int batch = 0; batch < TS_BATCHES; ++batch, ++batches) {
+            const int slot = (int)(batches % TS_A_SLOTS);
+            const uint32_t par = (uint32_t)((batches / TS_A_SLOTS) & 1);
+            mbar_wait(a_free + e * TS_A_SLOTS + slot, par ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < TS_BATCH; ++i) {
+              const int tap = batch * TS_BATCH + i;
+              if (tap < 9) {
+                const int shift_row = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1) + r;
+                const uint32_t t_slot = abase + (slot * TS_BATCH + i) * 32;
+                if (layer <= 3) gather_tap<32, LO_SS>(stage, shift_row, t_slot);
+                else gather_tap<16, LO_SS>(stage, shift_row, t_slot);
+              }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(a_ready + e * TS_A_SLOTS + slot);
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(stage_free + s);  // this warp is done reading the window
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------ epilogue groups (and the stem on the CUDA cores)
+    const int e = (warp - 12) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + (tid & 31);
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const uint32_t gbase = tmem_base + e * TS_GROUP_COLS + lane_off;
     mbar_wait(wbar, 0);
     const float* wstem = reinterpret_cast<const float*>(w_s + OFF_W[0]);
-    long long g = 0, c = 0, taps = 0, mine = 0;
+    long long g = 0, c = 0;
     for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
       const float* im = P.images + (size_t)image * 1024;
       for (int layer = 0; layer < TR_LAYERS; ++layer) {
         for (int tile = 0; tile < ENC_TILES; ++tile, ++g) {
           const long long cc = c;
           if (layer > 0) ++c;
-          // stem tiles alternate by the global item index, convolution tiles by the convolution counter (the
-          // issuer warps use the same rule)
           if (layer == 0 ? ((int)(g & 1) != e) : ((int)(cc & 1) != e)) continue;
           const int pos = tile * 128 + r;
           const bool valid = enc_valid(pos);
@@ -841,45 +956,20 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_ts(const __grid_co
             publish_tile(tile_done + tile);
             continue;
           }
-          // ---- gather the 9 shifted windows into the TMEM ring ----
-          const int s = (int)(cc % ENC_STAGES);
-          const uint32_t spar = (uint32_t)((cc / ENC_STAGES) & 1);
-          mbar_wait(full + s, spar);
-          const uint8_t* stage = stage0 + s * TR_STAGE_B;
-          for (int batch = 0; batch < 9 / TS_BATCH; ++batch, ++taps) {
-            const int slot = (int)(taps % TS_A_SLOTS);
-            const uint32_t par = (uint32_t)((taps / TS_A_SLOTS) & 1);
-            mbar_wait(a_free + e * TS_A_SLOTS + slot, par ^ 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int i = 0; i < TS_BATCH; ++i) {
-              const int tap = batch * TS_BATCH + i;
-              const int shift_row = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1) + r;
-              const uint32_t t_slot = gbase + 64 + (slot * TS_BATCH + i) * 32;
-              if (layer <= 3) gather_tap<32>(stage, shift_row, t_slot);
-              else gather_tap<16>(stage, shift_row, t_slot);
-            }
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(a_ready + e * TS_A_SLOTS + slot);
-          }
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(stage_free + s);  // this warp is done reading the window
-          // ---- epilogue ----
-          mbar_wait(mma_done + e, (uint32_t)(mine & 1));
-          ++mine;
+          const int ds = (int)(cc % TS_D_SLOTS);
+          const uint32_t dpar = (uint32_t)((cc / TS_D_SLOTS) & 1);
+          mbar_wait(mma_done + ds, dpar);
           tc_fence_after();
-          uint32_t d[32];
-          if (layer <= 2) load_accumulator<32>(gbase, d);
-          else load_accumulator<16>(gbase, reinterpret_cast<uint32_t(&)[16]>(d[0]));
-          tc_fence_before();
+          const uint32_t taddr = tmem_base + ds * 64 + lane_off;
           const float* bias_s = reinterpret_cast<const float*>(
               w_s + OFF_W[layer] + (layer <= 2 ? TR_W2_B - 128 : layer == 3 ? TR_W3_B - 64 : TR_W4_B - 64));
-          if (layer == 1) epilogue_conv<32>(d, bias_s, nullptr, true, valid, pos, st, nullptr, 0);
-          else if (layer == 2) epilogue_conv<32>(d, bias_s, sx, true, valid, pos, sy, nullptr, 0);
-          else if (layer == 3) epilogue_conv<16>(d, bias_s, nullptr, true, valid, pos, sx, nullptr, 0);
-          else epilogue_conv<16>(d, bias_s, nullptr, false, valid, pos, nullptr, P.out_nchw + (size_t)image * P.cout * 1024, P.cout);
+          if (layer == 1) epilogue_from_tmem<32>(taddr, bias_s, nullptr, true, valid, pos, st, nullptr, 0);
+          else if (layer == 2) epilogue_from_tmem<32>(taddr, bias_s, sx, true, valid, pos, sy, nullptr, 0);
+          else if (layer == 3) epilogue_from_tmem<16>(taddr, bias_s, nullptr, true, valid, pos, sx, nullptr, 0);
+          else epilogue_from_tmem<16>(taddr, bias_s, nullptr, false, valid, pos, nullptr, P.out_nchw + (size_t)image * P.cout * 1024, P.cout);
+          tc_fence_before();
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(tmem_free + ds);
           if (layer < 4) publish_tile(tile_done + layer * ENC_TILES + tile);
         }
       }
@@ -927,18 +1017,23 @@ int launch_enc_trunk(int n_images, int cout, const float* images, const void* we
   if (configured_dev != dev) {
     rc = opt_in_shared_memory(k_enc_trunk, &window);
     if (rc) return rc;
-    rc = opt_in_shared_memory(k_enc_trunk_ts, &window);
+    rc = opt_in_shared_memory(k_enc_trunk_ts<false>, &window);
+    if (rc) return rc;
+    rc = opt_in_shared_memory(k_enc_trunk_ts<true>, &window);
     if (rc) return rc;
     configured_dev = dev;
   }
   MMF_REQUIRE(smem <= window, "encoder trunk needs %zu B of shared memory (window %zu B)", smem, window);
   if (grid > n_images) grid = n_images;
-  // MMF_ENC_VARIANT: 0 = A operand read from shared memory by the MMAs (SS form, default: 5.25 ms per 16,384 images),
-  //                  1 = A through TMEM (TS form; parity-green but 7.0 ms: the gather -> publish -> MMA -> epilogue chain
-  //                      of only two tile groups leaves every unit < 35 % busy)
+  // MMF_ENC_VARIANT (all parity-green, measured per 16,384 images on B200):
+  //   0 = SS form: the MMAs read the shifted A windows from shared memory themselves (default, 5.25 ms)
+  //   1 = TS form: dedicated gather warps copy the windows into TMEM (LDS + tcgen05.st), MMAs read A from TMEM (5.7 ms:
+  //       the LSU shared-memory pipe becomes the busiest unit, 64 % in ncu)
+  //   2 = hybrid: hi halves through TMEM, lo halves read from shared memory by SS-form MMAs (5.5 ms)
   int variant = 0;
   if (const char* env = getenv("MMF_ENC_VARIANT")) variant = atoi(env);
-  if (variant == 1) k_enc_trunk_ts<<<grid, ENC_THREADS, smem, stream>>>(P);
+  if (variant == 1) k_enc_trunk_ts<false><<<grid, TS_THREADS, smem, stream>>>(P);
+  else if (variant == 2) k_enc_trunk_ts<true><<<grid, TS_THREADS, smem, stream>>>(P);
   else k_enc_trunk<<<grid, ENC_THREADS, smem, stream>>>(P);
   MMF_LAUNCH_CHECK("k_enc_trunk");
   return MMF_OK;
