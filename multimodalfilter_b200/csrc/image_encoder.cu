@@ -369,9 +369,9 @@ static int launch_conv(const ConvParams& P, cudaStream_t stream) {
 
 // ---- fused trunk: all five layers of one image by one CTA, activation maps in L2-resident scratch ---------------
 // The layer-by-layer kernels above stream every map through HBM (ncu: 3.7 TB/s, 57 % of peak, tensor pipe 26 %).
-// Here a persistent CTA carries an image through stem -> block1 -> block2(+x) -> 32->16 -> 16->8 by itself: its three
-// scratch maps (480 KB) are private, so 148 CTAs keep 71 MB hot in the 126 MB L2 and HBM only sees the raw image and
-// the final (8, 32, 32) activations.  Work items = (layer, tile) in order; tile t of layer l+1 only needs tiles
+// Here a persistent CTA carries an image through stem -> block1 -> block2(+x) -> 32->16 -> 16->8 by itself: its four
+// scratch maps (640 KB: x double-buffered, t/z, y) are private, so 148 CTAs keep 95 MB hot in the 126 MB L2 and HBM only
+// sees the raw image and the final (8, 32, 32) activations.  Work items = (layer, tile) in order; tile t of layer l+1 only needs tiles
 // t-1..t+1 of layer l, tracked by one mbarrier per (layer, tile), so the TMA -> MMA -> epilogue ring never drains
 // between layers.  Epilogue warps write the maps with generic stores and publish them to the async proxy
 // (fence.proxy.async.global + mbarrier release) before the producer's bulk copies read them.
@@ -383,11 +383,12 @@ constexpr int TR_W3_B = 2 * 9 * 4 * 16 * 16 + 64;    // 32->16
 constexpr int TR_W4_B = 2 * 9 * 2 * 16 * 16 + 64;    // 16->(<=16)
 constexpr int TR_WSTEM_B = (25 * 32 + 32) * 4;
 constexpr int TR_W_B = 2 * TR_W2_B + TR_W3_B + TR_W4_B + TR_WSTEM_B;
+constexpr int TR_SCRATCH_MAPS = 4;            // x (two buffers), t / z, y
 
 struct TrunkParams {
   const float* images;      // (n, 32, 32)
   const uint8_t* weights;   // [W block1 | W block2 | W 32->16 | W 16->8 | stem fp32], as packed for the layer kernels
-  uint8_t* scratch;         // gridDim.x * 3 * enc_map_bytes(32), zero-initialised once
+  uint8_t* scratch;         // gridDim.x * TR_SCRATCH_MAPS * enc_map_bytes(32), zero-initialised once
   float* out_nchw;          // (n, cout, 32, 32)
   int n_images, cout;
 };
@@ -446,8 +447,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
   uint64_t* stage_free = bars + 2 * ENC_STAGES;
   uint64_t* tmem_free = bars + 3 * ENC_STAGES;
   uint64_t* wbar = bars + 4 * ENC_STAGES;
-  uint64_t* tile_done = wbar + 1;  // [layer 0..3][tile]: that tile of the layer's OUTPUT map is written and published
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 4 * ENC_TILES);
+  uint64_t* stem_done = wbar + 1;                  // [x buffer 0|1][tile]: stem output of an image is written and published
+  uint64_t* tile_done = stem_done + 2 * ENC_TILES;  // [layer 1..3][tile]: that tile of the layer's OUTPUT map
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 3 * ENC_TILES);
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
       mbar_init(stage_free + s, 1);
       mbar_init(tmem_free + s, 4);
     }
-    for (int i = 0; i < 4 * ENC_TILES; ++i) mbar_init(tile_done + i, 4);
+    for (int i = 0; i < 5 * ENC_TILES; ++i) mbar_init(stem_done + i, 4);
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -474,8 +476,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const size_t map32 = enc_map_bytes(32);
-  uint8_t* sx = P.scratch + (size_t)blockIdx.x * 3 * map32;  // stem output x, later the 16-channel map z
-  uint8_t* st = sx + map32;                                   // block1 output
+  // x is double-buffered: the stem of image k+1 is computed in the shadow of image k's convolutions
+  uint8_t* sx0 = P.scratch + (size_t)blockIdx.x * TR_SCRATCH_MAPS * map32;
+  uint8_t* st = sx0 + 2 * map32;                              // block1 output, later the 16-channel map z
   uint8_t* sy = st + map32;                                   // resblock output
   // shared-memory offsets of the per-layer weights
   constexpr int OFF_W[5] = {2 * TR_W2_B + TR_W3_B + TR_W4_B, 0, TR_W2_B, 2 * TR_W2_B, 2 * TR_W2_B + TR_W3_B};
@@ -493,17 +496,19 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
       for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x, ++k) {
         const uint32_t ipar = (uint32_t)(k & 1);
         for (int layer = 1; layer <= 4; ++layer) {
-          const uint8_t* in = layer == 1 ? sx : layer == 2 ? st : layer == 3 ? sy : sx;
+          const uint8_t* in = layer == 1 ? sx0 + (size_t)(k & 1) * map32 : layer == 2 ? st : layer == 3 ? sy : st;
           const int planes = layer == 4 ? 4 : 8;
           for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
             const int s = (int)(c % ENC_STAGES);
             const uint32_t par = (uint32_t)((c / ENC_STAGES) & 1);
             mbar_wait(stage_free + s, par ^ 1u);
             // the window reaches into the neighbouring tiles of the producing layer
-            const uint64_t* dep = tile_done + (layer - 1) * ENC_TILES;
-            if (tile > 0) mbar_wait(const_cast<uint64_t*>(dep) + tile - 1, ipar);
-            mbar_wait(const_cast<uint64_t*>(dep) + tile, ipar);
-            if (tile + 1 < ENC_TILES) mbar_wait(const_cast<uint64_t*>(dep) + tile + 1, ipar);
+            // layer 1 reads the stem output in x[k & 1] (completed once every second image), the others layer - 1
+            uint64_t* dep = layer == 1 ? stem_done + (k & 1) * ENC_TILES : tile_done + (layer - 2) * ENC_TILES;
+            const uint32_t dpar = layer == 1 ? (uint32_t)((k >> 1) & 1) : ipar;
+            if (tile > 0) mbar_wait(dep + tile - 1, dpar);
+            mbar_wait(dep + tile, dpar);
+            if (tile + 1 < ENC_TILES) mbar_wait(dep + tile + 1, dpar);
             asm volatile("fence.proxy.async.global;" ::: "memory");
             const uint8_t* src = in + (size_t)(ENC_GUARD + tile * 128 - ENC_HALO) * 16;
             mbar_expect_tx(full + s, (uint32_t)planes * ENC_WIN_B);
@@ -547,56 +552,67 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
     const int r = quad * 32 + (tid & 31);
     mbar_wait(wbar, 0);
     const float* wstem = reinterpret_cast<const float*>(w_s + OFF_W[0]);
-    long long g = 0, c = 0;
-    for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
-      const float* im = P.images + (size_t)image * 1024;
-      for (int layer = 0; layer < TR_LAYERS; ++layer) {
-        for (int tile = 0; tile < ENC_TILES; ++tile, ++g) {
-          const long long cc = c;
-          if (layer > 0) ++c;
-          if ((int)(g & 1) != eg) continue;
+    // stem tile `tile` of image `img` (the kk-th image of this CTA) -> x[kk & 1]
+    auto stem_tile = [&](long long img, int kk, int tile) {
+      const float* im = P.images + (size_t)img * 1024;
+      uint8_t* sx = sx0 + (size_t)(kk & 1) * map32;
+      const int pos = tile * 128 + r;
+      const bool valid = enc_valid(pos);
+      float acc[32];
+#pragma unroll
+      for (int ch = 0; ch < 32; ++ch) acc[ch] = wstem[25 * 32 + ch];
+      if (valid) {
+        const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
+        for (int ky = 0; ky < 5; ++ky) {
+          const int yy = y + ky - 2;
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const int xx = x + kx - 2;
+            const float p = (yy >= 0 && yy < 32 && xx >= 0 && xx < 32) ? __ldg(im + yy * 32 + xx) : 0.0f;
+            const float4* w4 = reinterpret_cast<const float4*>(wstem + (ky * 5 + kx) * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = w4[q];
+              acc[4 * q] = fmaf(t.x, p, acc[4 * q]);
+              acc[4 * q + 1] = fmaf(t.y, p, acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(t.z, p, acc[4 * q + 2]);
+              acc[4 * q + 3] = fmaf(t.w, p, acc[4 * q + 3]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = valid ? fmaxf(acc[kc * 8 + j], 0.0f) : 0.0f;
+        uint4 hi4, lo4;
+        split8(v, hi4, lo4);
+        uint8_t* plane = sx + (size_t)(kc * 2) * ENC_PLANE_B + (size_t)(ENC_GUARD + pos) * 16;
+        *reinterpret_cast<uint4*>(plane) = hi4;
+        *reinterpret_cast<uint4*>(plane + ENC_PLANE_B) = lo4;
+      }
+      publish_tile(stem_done + (kk & 1) * ENC_TILES + tile);
+    };
+    // the first image's stem up front; afterwards the stem of image k+1 rides along with the convolution items of
+    // image k (one stem tile every fourth item), where the epilogue warps would otherwise wait for the tensor pipe
+    if ((long long)blockIdx.x < P.n_images)
+      for (int tile = 0; tile < ENC_TILES; ++tile)
+        if ((tile & 1) == eg) stem_tile(blockIdx.x, 0, tile);
+    long long c = 0;
+    int k = 0;
+    for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x, ++k) {
+      const long long next = image + gridDim.x;
+      const uint8_t* sx = sx0 + (size_t)(k & 1) * map32;
+      int j = 0;
+      for (int layer = 1; layer <= 4; ++layer) {
+        for (int tile = 0; tile < ENC_TILES; ++tile, ++c, ++j) {
+          if ((j & 3) == 0 && (j >> 2) < ENC_TILES && next < P.n_images && (((j >> 2) & 1) == eg)) stem_tile(next, k + 1, j >> 2);
+          if ((int)(c & 1) != eg) continue;
           const int pos = tile * 128 + r;
           const bool valid = enc_valid(pos);
-          if (layer == 0) {
-            float acc[32];
-#pragma unroll
-            for (int ch = 0; ch < 32; ++ch) acc[ch] = wstem[25 * 32 + ch];
-            if (valid) {
-              const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
-              for (int ky = 0; ky < 5; ++ky) {
-                const int yy = y + ky - 2;
-#pragma unroll
-                for (int kx = 0; kx < 5; ++kx) {
-                  const int xx = x + kx - 2;
-                  const float p = (yy >= 0 && yy < 32 && xx >= 0 && xx < 32) ? __ldg(im + yy * 32 + xx) : 0.0f;
-                  const float4* w4 = reinterpret_cast<const float4*>(wstem + (ky * 5 + kx) * 32);
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const float4 t = w4[q];
-                    acc[4 * q] = fmaf(t.x, p, acc[4 * q]);
-                    acc[4 * q + 1] = fmaf(t.y, p, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(t.z, p, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(t.w, p, acc[4 * q + 3]);
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = valid ? fmaxf(acc[kc * 8 + j], 0.0f) : 0.0f;
-              uint4 hi4, lo4;
-              split8(v, hi4, lo4);
-              uint8_t* plane = sx + (size_t)(kc * 2) * ENC_PLANE_B + (size_t)(ENC_GUARD + pos) * 16;
-              *reinterpret_cast<uint4*>(plane) = hi4;
-              *reinterpret_cast<uint4*>(plane + ENC_PLANE_B) = lo4;
-            }
-            publish_tile(tile_done + tile);
-            continue;
-          }
-          const int s = (int)(cc % ENC_STAGES);
-          const uint32_t par = (uint32_t)((cc / ENC_STAGES) & 1);
+          const int s = (int)(c % ENC_STAGES);
+          const uint32_t par = (uint32_t)((c / ENC_STAGES) & 1);
           mbar_wait(mma_done + s, par);
           tc_fence_after();
           uint32_t d[32];
@@ -610,9 +626,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
               w_s + OFF_W[layer] + (layer <= 2 ? TR_W2_B - 128 : layer == 3 ? TR_W3_B - 64 : TR_W4_B - 64));
           if (layer == 1) epilogue_conv<32>(d, bias_s, nullptr, true, valid, pos, st, nullptr, 0);
           else if (layer == 2) epilogue_conv<32>(d, bias_s, sx, true, valid, pos, sy, nullptr, 0);
-          else if (layer == 3) epilogue_conv<16>(d, bias_s, nullptr, true, valid, pos, sx, nullptr, 0);
+          else if (layer == 3) epilogue_conv<16>(d, bias_s, nullptr, true, valid, pos, st, nullptr, 0);
           else epilogue_conv<16>(d, bias_s, nullptr, false, valid, pos, nullptr, P.out_nchw + (size_t)image * P.cout * 1024, P.cout);
-          if (layer < 4) publish_tile(tile_done + layer * ENC_TILES + tile);
+          if (layer < 4) publish_tile(tile_done + (layer - 1) * ENC_TILES + tile);
         }
       }
     }
@@ -780,7 +796,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_enc_trunk_ts(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   const size_t map32 = enc_map_bytes(32);
-  uint8_t* sx = P.scratch + (size_t)blockIdx.x * 3 * map32;
+  uint8_t* sx = P.scratch + (size_t)blockIdx.x * TR_SCRATCH_MAPS * map32;
   uint8_t* st = sx + map32;
   uint8_t* sy = st + map32;
   constexpr int OFF_W[5] = {2 * TR_W2_B + TR_W3_B + TR_W4_B, 0, TR_W2_B, 2 * TR_W2_B, 2 * TR_W2_B + TR_W3_B};
@@ -994,7 +1010,7 @@ size_t enc_trunk_weight_bytes() { return TR_W_B; }
 size_t enc_trunk_scratch_bytes() {
   int grid = 148;
   trunk_grid(&grid);
-  return (size_t)grid * 3 * enc_map_bytes(32);
+  return (size_t)grid * TR_SCRATCH_MAPS * enc_map_bytes(32);
 }
 
 int launch_enc_trunk(int n_images, int cout, const float* images, const void* weights, void* scratch, float* out_nchw,

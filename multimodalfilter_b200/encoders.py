@@ -4,7 +4,8 @@
 ref: crossmodal/push_models/layers.py:93-104, crossmodal/door_models/layers.py:43-63); only its forward
 changes: under ``torch.no_grad()`` on a CUDA device the Conv2d layers run through ``mmf_enc_trunk`` (one launch,
 tensor cores, bf16 hi/lo split operands, fp32 accumulation) and the Flatten/Linear tail stays with torch.  With autograd enabled (encoder training / pre-training) the plain module path runs, so
-gradients are untouched.  There is no CPU variant of the fused trunk: on a CPU tensor the module is the
+gradients are untouched.  The trunk's scratch maps belong to the module instance and launches are ordered on the
+current stream: do not run the same encoder instance concurrently on two streams.  There is no CPU variant of the fused trunk: on a CPU tensor the module is the
 ordinary torch Sequential, exactly as in the reference.
 """
 import torch
