@@ -257,10 +257,16 @@ int mmf_enc_stem(int32_t n_images, const float* images, const float* w, void* ou
 int mmf_enc_conv3x3(int32_t n_images, int32_t cin, int32_t cout, const void* in_map, const void* w_image,
                     const void* res_map, int32_t relu, void* out_map, float* out_nchw, void* stream);
 
-/* dW_out (K, L, 64, 64) += delta[k][l]^T act[k][l] for the L 64x64 layers of every head (reduction over the
- * N*M rows, fp32); dW_out must be zero-initialised by the caller (partial tiles are combined atomically). */
-int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, const float* act, const float* delta,
-                              float* dW_out, void* stream);
+/* Parameter gradients of the heads from the saved activations and the deltas (both (K, L+1, 16, rows, 4)
+ * chunk-major planes: element [k][l][c][p][j] = column 4c+j of row p), fp32 reductions over the N*M rows:
+ *   dW_out   (K, L, 64, 64)  += delta[k][l]^T act[k][l]              the L 64x64 layers
+ *   db_out   (K, L+1, 64)    += column sums of delta[k][l]           (plane L = the input layer)
+ *   g_in_out (K, 64, sd)     += delta[k][L]^T x,  x = states (rows, sd)   input-layer weight
+ *   g_out_out(K, 64)         += act[k][L]^T d_ll[k],  d_ll (K, rows)      output-layer weight
+ * All outputs must be zero-initialised by the caller (partial sums are combined atomically). */
+int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, int32_t sd, const float* act, const float* delta,
+                              const float* x, const float* d_ll, float* dW_out, float* db_out, float* g_in_out,
+                              float* g_out_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -101,7 +101,7 @@ PROTOTYPES = {
     "mmf_pf_heads_forward_train": (
         C.c_int, [C.POINTER(PFModel), _i32, _i32, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp]),
     "mmf_pf_heads_backward": (C.c_int, [C.POINTER(PFModel), _i32, _i32, _vp, _vp, _u32, _vp, _vp]),
-    "mmf_pf_heads_weight_grads": (C.c_int, [_i32, _i32, C.c_int64, _vp, _vp, _vp, _vp]),
+    "mmf_pf_heads_weight_grads": (C.c_int, [_i32, _i32, C.c_int64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmf_enc_map_bytes": (_sz, [_i32]),
     "mmf_enc_trunk_scratch_bytes": (_sz, []),
     "mmf_enc_trunk_weight_bytes": (_sz, []),

@@ -273,11 +273,14 @@ int mmf_pf_heads_backward(const mmf_pf_model* model, int32_t N, int32_t M, const
   return launch_head_chain_bwd(model, N, M, act, d_ll, enabled_mask & all, delta_out, (cudaStream_t)stream);
 }
 
-int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, const float* act, const float* delta, float* dW_out,
-                              void* stream) {
-  MMF_REQUIRE(K >= 1 && K <= MMF_MAX_HEADS && L >= 1 && rows >= 0, "heads_weight_grads: bad shape K=%d L=%d", K, L);
-  MMF_REQUIRE(rows == 0 || (act && delta && dW_out), "heads_weight_grads: NULL buffer");
-  return launch_heads_dw(K, L, rows, act, delta, dW_out, (cudaStream_t)stream);
+int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, int32_t sd, const float* act, const float* delta,
+                              const float* x, const float* d_ll, float* dW_out, float* db_out, float* g_in_out,
+                              float* g_out_out, void* stream) {
+  MMF_REQUIRE(K >= 1 && K <= MMF_MAX_HEADS && L >= 1 && rows >= 0 && sd >= 1 && sd <= MMF_MAX_SD,
+              "heads_weight_grads: bad shape K=%d L=%d sd=%d", K, L, sd);
+  MMF_REQUIRE(rows == 0 || (act && delta && x && d_ll && dW_out && db_out && g_in_out && g_out_out),
+              "heads_weight_grads: NULL buffer");
+  return launch_heads_dw(K, L, rows, sd, act, delta, x, d_ll, dW_out, db_out, g_in_out, g_out_out, (cudaStream_t)stream);
 }
 
 size_t mmf_enc_map_bytes(int32_t channels) { return enc_map_bytes_host(channels); }

@@ -58,7 +58,8 @@ size_t chain_bwd_bytes(const mmf_chain* chain);
 int pack_chain_bwd(const mmf_chain* chain, void* dst, cudaStream_t stream);
 int launch_head_chain_bwd(const mmf_pf_model* model, int N, int M, const float* act, const float* d_ll, uint32_t enabled,
                           float* delta_out, cudaStream_t stream);
-int launch_heads_dw(int K, int L, long long P, const float* act, const float* delta, float* dW, cudaStream_t stream);
+int launch_heads_dw(int K, int L, long long P, int sd, const float* act, const float* delta, const float* x,
+                    const float* d_ll, float* dW, float* db, float* g_in, float* g_out, cudaStream_t stream);
 size_t enc_map_bytes_host(int channels);
 size_t enc_trunk_weight_bytes();
 size_t enc_trunk_scratch_bytes();

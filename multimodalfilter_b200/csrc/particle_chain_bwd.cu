@@ -94,13 +94,15 @@ __device__ __forceinline__ int layer_kind(const ChainDev& ch, int layer) {
 
 // One 16-column slice of "next delta = (grad [+ skip]) * relu'(activation)": stores it, keeps the skip branch,
 // and (feed != 0) writes it as the next A operand.
+// act_row / delta_row point at this row's float4 of column chunk 0 in the chunk-major planes (see store_act_chunk in
+// particle_chain_tc.cu); stride4 = rows * 4 floats separates the column chunks.
 __device__ __forceinline__ void delta_chunk(float2 (&v)[8], const float* __restrict__ act_row, float* __restrict__ delta_row,
-                                            float2 (&gres)[U / 2], int chunk, bool add_res, bool mask, bool set_res,
-                                            bool feed, uint32_t tAhi, uint32_t tAlo) {
-  const float4* a4 = reinterpret_cast<const float4*>(act_row + chunk * 16);
+                                            size_t stride4, float2 (&gres)[U / 2], int chunk, bool add_res, bool mask,
+                                            bool set_res, bool feed, uint32_t tAhi, uint32_t tAlo) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 a = mask ? __ldg(a4 + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 a = mask ? __ldg(reinterpret_cast<const float4*>(act_row + (size_t)(chunk * 4 + q) * stride4))
+                          : make_float4(1.f, 1.f, 1.f, 1.f);
     float2 g0 = v[2 * q], g1 = v[2 * q + 1];
     if (add_res) {
       g0 = __fadd2_rn(g0, gres[chunk * 8 + 2 * q]);
@@ -118,9 +120,10 @@ __device__ __forceinline__ void delta_chunk(float2 (&v)[8], const float* __restr
     }
   }
   if (delta_row != nullptr) {
-    float4* d4 = reinterpret_cast<float4*>(delta_row + chunk * 16);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(delta_row + (size_t)(chunk * 4 + q) * stride4) =
+          make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
   }
   if (feed) store_a_chunk<false>(v, tAhi, tAlo, chunk, false);
 }
@@ -181,8 +184,9 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_head_chain_bwd(const __g
       const long long p_raw = tile * 128 + row;
       const bool live = p_raw < P.total;
       const long long p = live ? p_raw : P.total - 1;
-      const float* act_base = P.act + ((size_t)k * (L + 1) * P.total + (size_t)p) * U;
-      float* delta_base = P.delta_out + ((size_t)k * (L + 1) * P.total + (size_t)p) * U;
+      const float* act_base = P.act + (size_t)k * (L + 1) * P.total * U + (size_t)p * 4;
+      float* delta_base = P.delta_out + (size_t)k * (L + 1) * P.total * U + (size_t)p * 4;
+      const size_t stride4 = (size_t)P.total * 4;
       const float dll = live ? P.d_ll[(size_t)k * P.total + p] : 0.0f;
 
       // ---- output layer: grad w.r.t. its input = dll * out_W[0]; delta of layer L-1 -------------------------
@@ -202,8 +206,8 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_head_chain_bwd(const __g
             v[2 * q] = make_float2(w.x * dll, w.y * dll);
             v[2 * q + 1] = make_float2(w.z * dll, w.w * dll);
           }
-          delta_chunk(v, act_base + (size_t)L * plane, live ? delta_base + (size_t)(L - 1) * plane : nullptr, gres, chunk,
-                      false, mask, kind == LK_RES_B, true, tAhi, tAlo);
+          delta_chunk(v, act_base + (size_t)L * plane, live ? delta_base + (size_t)(L - 1) * plane : nullptr, stride4, gres,
+                      chunk, false, mask, kind == LK_RES_B, true, tAhi, tAlo);
         }
       }
 
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_head_chain_bwd(const __g
           float2 v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = make_float2(__uint_as_float(d[2 * j]), __uint_as_float(d[2 * j + 1]));
-          delta_chunk(v, arow, drow, gres, chunk, add_res, mask, set_res, prod >= 0, tAhi, tAlo);
+          delta_chunk(v, arow, drow, stride4, gres, chunk, add_res, mask, set_res, prod >= 0, tAhi, tAlo);
         }
       }
     }
@@ -312,10 +316,10 @@ constexpr int DW_ROWS = 32;      // rows staged per iteration
 constexpr int DW_THREADS = 256;  // each thread owns a 4 x 4 block of the 64 x 64 output
 
 __global__ void __launch_bounds__(DW_THREADS) k_heads_dw(const float* __restrict__ act, const float* __restrict__ delta,
-                                                         float* __restrict__ dW, long long P, int planes_per_head,
-                                                         int L, int rows_per_cta) {
-  __shared__ __align__(16) float sa[DW_ROWS][U];
-  __shared__ __align__(16) float sd[DW_ROWS][U];
+                                                         float* __restrict__ dW, float* __restrict__ db, long long P,
+                                                         int planes_per_head, int L, int rows_per_cta) {
+  __shared__ __align__(16) float sa[DW_ROWS][U + 4];  // +4: rows 4 banks apart for the column-chunk-wise staging stores
+  __shared__ __align__(16) float sd[DW_ROWS][U + 4];
   const int layer = blockIdx.y, head = blockIdx.z;
   const size_t plane = ((size_t)head * planes_per_head + layer) * (size_t)P * U;
   const float* A = act + plane;
@@ -325,45 +329,132 @@ __global__ void __launch_bounds__(DW_THREADS) k_heads_dw(const float* __restrict
   const int tid = threadIdx.x;
   const int jo = (tid >> 4) * 4;  // output-feature block (rows of dW)
   const int io = (tid & 15) * 4;  // input-feature block  (cols of dW)
-  float acc[4][4];
+  float2 acc[4][2];  // packed fp32x2 accumulators: acc[a][h] = columns io + 2h, io + 2h + 1 of row jo + a
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+    for (int h = 0; h < 2; ++h) acc[a][h] = make_float2(0.0f, 0.0f);
+  float colsum = 0.0f;  // bias gradient of column `tid` (threads 0..63): sum of delta over the rows
 
-  for (long long r = row0; r < row1; r += DW_ROWS) {
-    __syncthreads();
-    // 32 rows x 64 floats = 512 float4 per operand; 256 threads x 2
+  // 32 rows x 64 floats = 512 float4 per operand = 2 per thread; a warp reads 32 consecutive rows of one column chunk
+  // (chunk-major planes).  The loads of tile t+1 are issued before tile t is consumed (register double buffer).
+  float4 va[2], vd[2];
+  auto fetch = [&](long long r) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * DW_THREADS;  // float4 index
-      const int rr = e >> 4, c4 = e & 15;
+      const int e = tid + q * DW_THREADS;
+      const int c4 = e >> 5, rr = e & 31;
       const bool ok = r + rr < row1;
-      const float4 va = ok ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(r + rr) * U) + c4) : make_float4(0, 0, 0, 0);
-      const float4 vd = ok ? __ldg(reinterpret_cast<const float4*>(D + (size_t)(r + rr) * U) + c4) : make_float4(0, 0, 0, 0);
-      reinterpret_cast<float4*>(&sa[rr][0])[c4] = va;
-      reinterpret_cast<float4*>(&sd[rr][0])[c4] = vd;
+      const size_t off = ((size_t)c4 * P + (size_t)(r + rr)) * 4;
+      va[q] = ok ? __ldg(reinterpret_cast<const float4*>(A + off)) : make_float4(0, 0, 0, 0);
+      vd[q] = ok ? __ldg(reinterpret_cast<const float4*>(D + off)) : make_float4(0, 0, 0, 0);
+    }
+  };
+  if (row0 < row1) fetch(row0);
+  for (long long r = row0; r < row1; r += DW_ROWS) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * DW_THREADS;
+      const int c4 = e >> 5, rr = e & 31;
+      reinterpret_cast<float4*>(&sa[rr][0])[c4] = va[q];
+      reinterpret_cast<float4*>(&sd[rr][0])[c4] = vd[q];
     }
     __syncthreads();
+    if (r + DW_ROWS < row1) fetch(r + DW_ROWS);
+    if (tid < U) {
+#pragma unroll 8
+      for (int rr = 0; rr < DW_ROWS; ++rr) colsum += sd[rr][tid];
+    }
 #pragma unroll 8
     for (int rr = 0; rr < DW_ROWS; ++rr) {
       const float4 dv = *reinterpret_cast<const float4*>(&sd[rr][jo]);
       const float4 av = *reinterpret_cast<const float4*>(&sa[rr][io]);
-      const float dj[4] = {dv.x, dv.y, dv.z, dv.w}, ai[4] = {av.x, av.y, av.z, av.w};
+      const float dj[4] = {dv.x, dv.y, dv.z, dv.w};
+      const float2 a01 = make_float2(av.x, av.y), a23 = make_float2(av.z, av.w);
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dj[a], ai[b], acc[a][b]);
+      for (int a = 0; a < 4; ++a) {  // FFMA2: two FMAs per issue slot
+        const float2 d2 = make_float2(dj[a], dj[a]);
+        acc[a][0] = __ffma2_rn(d2, a01, acc[a][0]);
+        acc[a][1] = __ffma2_rn(d2, a23, acc[a][1]);
+      }
     }
   }
   float* out = dW + ((size_t)head * L + layer) * U * U;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) atomicAdd(out + (size_t)(jo + a) * U + io + b, acc[a][b]);
+  for (int a = 0; a < 4; ++a) {
+    atomicAdd(out + (size_t)(jo + a) * U + io + 0, acc[a][0].x);
+    atomicAdd(out + (size_t)(jo + a) * U + io + 1, acc[a][0].y);
+    atomicAdd(out + (size_t)(jo + a) * U + io + 2, acc[a][1].x);
+    atomicAdd(out + (size_t)(jo + a) * U + io + 3, acc[a][1].y);
+  }
+  if (tid < U) atomicAdd(db + ((size_t)head * planes_per_head + layer) * U + tid, colsum);
 }
 
-int launch_heads_dw(int K, int L, long long P, const float* act, const float* delta, float* dW, cudaStream_t stream) {
+// Gradients of the two thin layers at the ends of a head, one pass over plane L of delta and act:
+//   g_in[k][j][d] = sum_p delta_in[p][j] * x[p][d]   (input layer weight, x = particle states)
+//   db[k][L][j]   = sum_p delta_in[p][j]             (input layer bias)
+//   g_out[k][j]   = sum_p d_ll[p] * a_L[p][j]        (output layer weight)
+// thread = (column chunk c4, row lane): 16 consecutive rows of one chunk per half warp (coalesced 256 B).
+__global__ void __launch_bounds__(256) k_heads_edge_grads(const float* __restrict__ act, const float* __restrict__ delta,
+                                                          const float* __restrict__ x, const float* __restrict__ d_ll,
+                                                          float* __restrict__ g_in, float* __restrict__ db,
+                                                          float* __restrict__ g_out, long long P, int L, int sd,
+                                                          int rows_per_cta) {
+  const int head = blockIdx.y;
+  const size_t plane = ((size_t)head * (L + 1) + L) * (size_t)P * U;
+  const float* A = act + plane;
+  const float* D = delta + plane;
+  const int c4 = threadIdx.x >> 4, lane16 = threadIdx.x & 15;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta;
+  const long long row1 = row0 + rows_per_cta < P ? row0 + rows_per_cta : P;
+  float gi[4][MMF_MAX_SD], gb[4] = {0.f, 0.f, 0.f, 0.f}, go[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int d = 0; d < MMF_MAX_SD; ++d) gi[j][d] = 0.0f;
+  for (long long p = row0 + lane16; p < row1; p += 16) {
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(D + ((size_t)c4 * P + (size_t)p) * 4));
+    const float4 av = __ldg(reinterpret_cast<const float4*>(A + ((size_t)c4 * P + (size_t)p) * 4));
+    const float w = __ldg(d_ll + (size_t)head * P + p);
+    const float dj[4] = {dv.x, dv.y, dv.z, dv.w}, aj[4] = {av.x, av.y, av.z, av.w};
+    float xs[MMF_MAX_SD];
+#pragma unroll
+    for (int d = 0; d < MMF_MAX_SD; ++d) xs[d] = d < sd ? __ldg(x + (size_t)p * sd + d) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      gb[j] += dj[j];
+      go[j] = fmaf(w, aj[j], go[j]);
+#pragma unroll
+      for (int d = 0; d < MMF_MAX_SD; ++d) gi[j][d] = fmaf(dj[j], xs[d], gi[j][d]);
+    }
+  }
+  // reduce over the 16 row lanes of this column chunk (they share a half warp)
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      gb[j] += __shfl_xor_sync(0xffffffffu, gb[j], o);
+      go[j] += __shfl_xor_sync(0xffffffffu, go[j], o);
+#pragma unroll
+      for (int d = 0; d < MMF_MAX_SD; ++d) gi[j][d] += __shfl_xor_sync(0xffffffffu, gi[j][d], o);
+    }
+  }
+  if (lane16 == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = c4 * 4 + j;
+      atomicAdd(db + ((size_t)head * (L + 1) + L) * U + col, gb[j]);
+      atomicAdd(g_out + (size_t)head * U + col, go[j]);
+#pragma unroll
+      for (int d = 0; d < MMF_MAX_SD; ++d)
+        if (d < sd) atomicAdd(g_in + ((size_t)head * U + col) * sd + d, gi[j][d]);
+    }
+  }
+}
+
+int launch_heads_dw(int K, int L, long long P, int sd, const float* act, const float* delta, const float* x,
+                    const float* d_ll, float* dW, float* db, float* g_in, float* g_out, cudaStream_t stream) {
   if (P == 0) return MMF_OK;
   int dev = 0, sms = 148;
   MMF_CUDA(cudaGetDevice(&dev));
@@ -374,8 +465,15 @@ int launch_heads_dw(int K, int L, long long P, const float* act, const float* de
   rows_per_cta = ((rows_per_cta + DW_ROWS - 1) / DW_ROWS) * DW_ROWS;
   chunks = (P + rows_per_cta - 1) / rows_per_cta;
   dim3 grid((unsigned)chunks, (unsigned)L, (unsigned)K);
-  k_heads_dw<<<grid, DW_THREADS, 0, stream>>>(act, delta, dW, P, L + 1, L, (int)rows_per_cta);
+  k_heads_dw<<<grid, DW_THREADS, 0, stream>>>(act, delta, dW, db, P, L + 1, L, (int)rows_per_cta);
   MMF_LAUNCH_CHECK("k_heads_dw");
+  long long edge_chunks = ((long long)sms * 4 + K - 1) / K;
+  long long edge_rows = (P + edge_chunks - 1) / edge_chunks;
+  edge_rows = ((edge_rows + 15) / 16) * 16;
+  edge_chunks = (P + edge_rows - 1) / edge_rows;
+  k_heads_edge_grads<<<dim3((unsigned)edge_chunks, (unsigned)K), 256, 0, stream>>>(act, delta, x, d_ll, g_in, db, g_out, P, L,
+                                                                                   sd, (int)edge_rows);
+  MMF_LAUNCH_CHECK("k_heads_edge_grads");
   return MMF_OK;
 }
 

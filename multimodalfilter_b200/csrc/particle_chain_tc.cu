@@ -137,15 +137,20 @@ enum { EPI_RES_A = 0, EPI_RES_B = 1, EPI_MID_RELU = 2, EPI_MID_LINEAR = 3 };
 //   MID_* : v = [relu](D + rowbias)   xr = v      (bias4 then points at the per-trajectory row in global memory)
 // tD / tAhi / tAlo / bias4 already point at this thread's first column.
 // store 16 activations of this thread's row (training: kept for the backward pass)
-__device__ __forceinline__ void store_act_chunk(float* act_row, int chunk, const float2 (&v)[8]) {
-  float4* dst = reinterpret_cast<float4*>(act_row + chunk * 16);
+// The saved activations (and the deltas of the backward kernel) are stored CHUNK-MAJOR: plane[c4][row][4 floats],
+// c4 = column / 4, so that the 32 rows of a warp write 512 contiguous bytes per store instruction (row-major
+// 256-byte rows cost one 32-byte sector per thread per instruction and saturated the LSU: ncu, r01).
+// act_row points at this row's float4 of column chunk 0; stride4 = rows * 4 floats separates column chunks.
+__device__ __forceinline__ void store_act_chunk(float* act_row, int chunk, const float2 (&v)[8], size_t stride4) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<float4*>(act_row + (size_t)(chunk * 4 + q) * stride4) =
+        make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
 }
 
 template <int KIND, int COLS>
 __device__ __forceinline__ void epilogue(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float4* __restrict__ bias4,
-                                         float2 (&xr)[COLS / 2], bool single_pass, float* act_row) {
+                                         float2 (&xr)[COLS / 2], bool single_pass, float* act_row, size_t act_stride4) {
   constexpr int CHUNKS = COLS / 16;
   // software pipeline over the accumulator chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c
   // is processed (tcgen05.wait::ld waits for ALL outstanding loads, so it is issued after the compute block)
@@ -179,7 +184,7 @@ __device__ __forceinline__ void epilogue(uint32_t tD, uint32_t tAhi, uint32_t tA
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = make_float2(fmaxf(v[j].x, 0.0f), fmaxf(v[j].y, 0.0f));
       }
-      store_act_chunk(act_row, chunk, v);
+      store_act_chunk(act_row, chunk, v, act_stride4);
     }
     if (KIND == EPI_RES_A) store_a_chunk<true>(v, tAhi, tAlo, chunk, single_pass);  // relu folded into the cvt
     else store_a_chunk<false>(v, tAhi, tAlo, chunk, single_pass);
@@ -305,9 +310,10 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
 
       // training: base of this particle's saved activations for head c (layer index selects the plane)
       float* act_base = (P.act_out != nullptr && c > 0 && live)
-                            ? P.act_out + ((size_t)(c - 1) * (L + 1) * P.total + (size_t)p) * U
+                            ? P.act_out + (size_t)(c - 1) * (L + 1) * P.total * U + (size_t)p * 4
                             : nullptr;
       const size_t act_plane = (size_t)P.total * U;
+      const size_t act_stride4 = (size_t)P.total * 4;
 
       // ---- input layer on the CUDA cores: xr = relu(in_W x + in_b) -> A operand ------------------------
       float2 xr[TC_COLS / 2];
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
             v[j].y = fmaxf(v[j].y, 0.0f);
             xr[chunk * 8 + j] = v[j];
           }
-          if (act_base != nullptr) store_act_chunk(act_base, chunk, v);
+          if (act_base != nullptr) store_act_chunk(act_base, chunk, v, act_stride4);
           store_a_chunk<false>(v, tAhi, tAlo, chunk, single_pass);
         }
       }
@@ -420,14 +426,14 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
         if (layer == mid_at) {
           const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
           float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane : nullptr;
-          if (ch.mid_relu) epilogue<EPI_MID_RELU, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass, arow);
-          else epilogue<EPI_MID_LINEAR, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass, arow);
+          if (ch.mid_relu) epilogue<EPI_MID_RELU, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4);
+          else epilogue<EPI_MID_LINEAR, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4);
         } else {
           const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
           const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U);
           float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane : nullptr;
-          if ((rel & 1) == 0) epilogue<EPI_RES_A, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass, arow);
-          else epilogue<EPI_RES_B, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass, arow);
+          if ((rel & 1) == 0) epilogue<EPI_RES_A, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass, arow, act_stride4);
+          else epilogue<EPI_RES_B, TC_COLS>(tD, tAhi, tAlo, bsm, xr, single_pass, arow, act_stride4);
         }
       }
 
@@ -506,7 +512,7 @@ __device__ __forceinline__ void publish_chunk(uint64_t* cbar, int chunk) {
 // tbuf / bias4 / act_row / cbar already point at this thread's first column (chunk); NCH chunks of 16 columns
 template <int KIND, int NCH>
 __device__ __forceinline__ void epilogue_pipe(uint32_t tbuf, const float4* __restrict__ bias4, float2 (&xr)[NCH * 8],
-                                              bool single_pass, float* act_row, uint64_t* cbar) {
+                                              bool single_pass, float* act_row, size_t act_stride4, uint64_t* cbar) {
   uint32_t d[2][16];
   tmem_ld16(tbuf, d[0]);
   tc_wait_ld();
@@ -537,7 +543,7 @@ __device__ __forceinline__ void epilogue_pipe(uint32_t tbuf, const float4* __res
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = make_float2(fmaxf(v[j].x, 0.0f), fmaxf(v[j].y, 0.0f));
       }
-      store_act_chunk(act_row, chunk, v);
+      store_act_chunk(act_row, chunk, v, act_stride4);
     }
     // in place: hi -> columns [16 chunk, +8), lo -> [16 chunk + 8, +8) of the buffer just read
     // chunk-1's stores have had this chunk's arithmetic to retire: publish it now, then store this chunk
@@ -690,9 +696,10 @@ __global__ void __launch_bounds__(TC_GROUPS * (128 * TPR + 32), 1) k_particle_ch
 #pragma unroll
       for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
       float* act_base = (P.act_out != nullptr && c > 0 && live)
-                            ? P.act_out + ((size_t)(c - 1) * (L + 1) * P.total + (size_t)p) * U
+                            ? P.act_out + (size_t)(c - 1) * (L + 1) * P.total * U + (size_t)p * 4
                             : nullptr;
       const size_t act_plane = (size_t)P.total * U;
+      const size_t act_stride4 = (size_t)P.total * 4;
 
       // input layer on the CUDA cores -> A operand in the current half, published chunk by chunk
       float2 xr[NCH * 8];
@@ -700,7 +707,7 @@ __global__ void __launch_bounds__(TC_GROUPS * (128 * TPR + 32), 1) k_particle_ch
         const uint32_t tbuf = tG + cur * 64 + col0;
         const float4* b4 = reinterpret_cast<const float4*>(in_b + col0);
         const float4* w4 = reinterpret_cast<const float4*>(in_Wt + col0);
-        float* act0 = act_base ? act_base + col0 : nullptr;
+        float* act0 = act_base ? act_base + (size_t)(col0 / 4) * act_stride4 : nullptr;
 #pragma unroll
         for (int chunk = 0; chunk < NCH; ++chunk) {
           float2 v[8];
@@ -728,7 +735,7 @@ __global__ void __launch_bounds__(TC_GROUPS * (128 * TPR + 32), 1) k_particle_ch
             v[j].y = fmaxf(v[j].y, 0.0f);
             xr[chunk * 8 + j] = v[j];
           }
-          if (act0 != nullptr) store_act_chunk(act0, chunk, v);
+          if (act0 != nullptr) store_act_chunk(act0, chunk, v, act_stride4);
           if (chunk > 0) publish_chunk(my_cbar, chunk - 1);
           store_a_chunk<false>(v, tbuf + chunk * 8, tbuf + chunk * 8 + 8, chunk, single_pass);
         }
@@ -742,16 +749,16 @@ __global__ void __launch_bounds__(TC_GROUPS * (128 * TPR + 32), 1) k_particle_ch
         tc_fence_after();
         if (layer == L) break;
         const uint32_t tbuf = tG + cur * 64 + col0;
-        float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane + col0 : nullptr;
+        float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane + (size_t)(col0 / 4) * act_stride4 : nullptr;
         if (layer == mid_at) {
           const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U + col0);
-          if (ch.mid_relu) epilogue_pipe<EPI_MID_RELU, NCH>(tbuf, brow, xr, single_pass, arow, my_cbar);
-          else epilogue_pipe<EPI_MID_LINEAR, NCH>(tbuf, brow, xr, single_pass, arow, my_cbar);
+          if (ch.mid_relu) epilogue_pipe<EPI_MID_RELU, NCH>(tbuf, brow, xr, single_pass, arow, act_stride4, my_cbar);
+          else epilogue_pipe<EPI_MID_LINEAR, NCH>(tbuf, brow, xr, single_pass, arow, act_stride4, my_cbar);
         } else {
           const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
           const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U + col0);
-          if ((rel & 1) == 0) epilogue_pipe<EPI_RES_A, NCH>(tbuf, bsm, xr, single_pass, arow, my_cbar);
-          else epilogue_pipe<EPI_RES_B, NCH>(tbuf, bsm, xr, single_pass, arow, my_cbar);
+          if ((rel & 1) == 0) epilogue_pipe<EPI_RES_A, NCH>(tbuf, bsm, xr, single_pass, arow, act_stride4, my_cbar);
+          else epilogue_pipe<EPI_RES_B, NCH>(tbuf, bsm, xr, single_pass, arow, act_stride4, my_cbar);
         }
       }
 

@@ -106,7 +106,8 @@ def head_depth(model_struct):
 def pf_heads_forward_train(model_struct, states, eps, rowbias, enabled_mask, precision=PREC_BF16X3):
     """Training forward of one step: move the particles (dynamics, frozen) and evaluate the heads, saving the
     activations the backward needs.  states (N,M,sd), eps (N*M,sd), rowbias (1+K,N,64) ->
-    moved (N,M,sd), ll (K,N,M), act (K,L+1,N*M,64)."""
+    moved (N,M,sd), ll (K,N,M), act (K,L+1,16,N*M,4): chunk-major planes, act[k,l,c,p,:] = columns 4c..4c+3 of row p
+    (coalesced for thread-per-row kernels; ``rows_view`` gives the (.., N*M, 64) matrix)."""
     lib = _lib.load()
     N, M, sd = states.shape
     K, L = model_struct.num_heads, head_depth(model_struct)
@@ -114,7 +115,7 @@ def pf_heads_forward_train(model_struct, states, eps, rowbias, enabled_mask, pre
     dev = states.device
     moved = torch.empty_like(states)
     ll = torch.full((K, N, M), float("nan"), device=dev, dtype=torch.float32)
-    act = torch.empty((K, L + 1, N * M, _lib.UNITS), device=dev, dtype=torch.float32)
+    act = torch.empty((K, L + 1, _lib.UNITS // 4, N * M, 4), device=dev, dtype=torch.float32)
     scratch = torch.empty((N, M), device=dev, dtype=torch.float32)
     _lib.check(
         PROFILE.run("pf_heads_forward_train", 1, lib.mmf_pf_heads_forward_train, C.byref(model_struct), N, M,
@@ -125,7 +126,8 @@ def pf_heads_forward_train(model_struct, states, eps, rowbias, enabled_mask, pre
 
 
 def pf_heads_backward(model_struct, N, M, act, d_ll, enabled_mask):
-    """d_ll (K,N,M) -> delta (K,L+1,N*M,64): plane l = delta of 64x64 layer l, plane L = delta of the input layer."""
+    """d_ll (K,N,M) -> delta (K,L+1,16,N*M,4) (chunk-major like act): plane l = delta of 64x64 layer l, plane L = delta
+    of the input layer."""
     lib = _lib.load()
     act, d_ll = _f32c(act), _f32c(d_ll)
     delta = torch.empty_like(act)  # every plane of every enabled head is fully written by the kernel
@@ -136,16 +138,30 @@ def pf_heads_backward(model_struct, N, M, act, d_ll, enabled_mask):
     return delta
 
 
-def pf_heads_weight_grads(act, delta):
-    """act, delta (K, L+1, P, 64) -> dW (K, L, 64, 64) with dW[k, l] = delta[k, l]^T act[k, l]."""
+def rows_view(t):
+    """(..., 16, P, 4) chunk-major planes -> (..., P, 64) row matrices (a copy; for tests and debugging)."""
+    return t.transpose(-3, -2).reshape(*t.shape[:-3], t.shape[-2], t.shape[-3] * t.shape[-1])
+
+
+def pf_heads_weight_grads(act, delta, states, d_ll):
+    """act, delta (K, L+1, 16, P, 4), states (P, sd), d_ll (K, P) -> parameter gradients of every head:
+    dW (K, L, 64, 64) = delta_l^T a_l, db (K, L+1, 64) = column sums of delta (plane L: the input layer),
+    g_in (K, 64, sd) = delta_L^T states, g_out (K, 64) = a_L^T d_ll."""
     lib = _lib.load()
-    K, Lp1, P, _ = act.shape
-    dW = torch.zeros((K, Lp1 - 1, _lib.UNITS, _lib.UNITS), device=act.device, dtype=torch.float32)
+    K, Lp1, _, P, _ = act.shape
+    sd = states.shape[1]
+    dev, U = act.device, _lib.UNITS
+    dW = torch.zeros((K, Lp1 - 1, U, U), device=dev, dtype=torch.float32)
+    db = torch.zeros((K, Lp1, U), device=dev, dtype=torch.float32)
+    g_in = torch.zeros((K, U, sd), device=dev, dtype=torch.float32)
+    g_out = torch.zeros((K, U), device=dev, dtype=torch.float32)
+    states, d_ll = _f32c(states), _f32c(d_ll)
     _lib.check(
-        PROFILE.run("pf_heads_weight_grads", 1, lib.mmf_pf_heads_weight_grads, K, Lp1 - 1, P, _lib.ptr(act),
-                    _lib.ptr(delta), _lib.ptr(dW), _lib.stream_of(act))
+        PROFILE.run("pf_heads_weight_grads", 2, lib.mmf_pf_heads_weight_grads, K, Lp1 - 1, P, sd, _lib.ptr(act),
+                    _lib.ptr(delta), _lib.ptr(states), _lib.ptr(d_ll), _lib.ptr(dW), _lib.ptr(db), _lib.ptr(g_in),
+                    _lib.ptr(g_out), _lib.stream_of(act))
     )
-    return dW
+    return dW, db, g_in, g_out
 
 
 # ---- image encoder trunk ------------------------------------------------------------------------------------

@@ -36,16 +36,11 @@ def head_parameters(spec) -> List[torch.Tensor]:
     return ps
 
 
-def _grads_for_head(spec, act, delta, dW, d_ll, moved_flat):
-    """act/delta: (L+1, P, 64); dW: (L, 64, 64) from mmf_pf_heads_weight_grads; d_ll: (P,); moved_flat: (P, sd).
-    Returns grads in head_parameters order."""
+def _grads_for_head(spec, dW, db, g_in, g_out, d_ll):
+    """dW (L, 64, 64), db (L+1, 64), g_in (64, sd), g_out (64,) from mmf_pf_heads_weight_grads; d_ll (P,).
+    Returns grads in head_parameters order and the index of the mid layer."""
     (in_lin, pre), (mid, post, out) = spec.state, spec.shared
     L = 2 * len(pre) + 1 + 2 * len(post)
-    db = delta.sum(dim=1)  # (L+1, 64)
-    # reductions over the P = N*M rows with a handful of output columns: gemv (bandwidth-bound) instead of a GEMM
-    # whose K = P dimension sends the library to a slow SIMT split
-    sd = moved_flat.shape[1]
-    g_in = torch.stack([torch.mv(delta[L].t(), moved_flat[:, d].contiguous()) for d in range(sd)], dim=1)
     grads = [g_in, db[L]]
     layer = 0
     for _ in pre:
@@ -61,7 +56,7 @@ def _grads_for_head(spec, act, delta, dW, d_ll, moved_flat):
         for _half in range(2):
             grads += [dW[layer], db[layer]]
             layer += 1
-    grads += [torch.mv(act[L].t(), d_ll)[None, :], d_ll.sum().reshape(1)]
+    grads += [g_out[None, :], d_ll.sum().reshape(1)]
     return grads, mid_layer
 
 
@@ -93,8 +88,8 @@ class FusedHeads(torch.autograd.Function):
                 if not (mask >> k) & 1:
                     delta[k].zero_()
                     act[k].zero_()
-        dW = ops.pf_heads_weight_grads(act, delta)
         moved_flat = moved.reshape(N * M, sd)
+        dW, db, g_in, g_out = ops.pf_heads_weight_grads(act, delta, moved_flat, d_ll.reshape(plan.K, N * M))
         d_rows = torch.zeros((plan.K, N, U), device=act.device, dtype=torch.float32)
         grads = []
         for k, spec in enumerate(plan.heads):
@@ -102,9 +97,9 @@ class FusedHeads(torch.autograd.Function):
             if not (mask >> k) & 1:
                 grads += [None] * n_params
                 continue
-            g, mid_layer = _grads_for_head(spec, act[k], delta[k], dW[k], d_ll[k].reshape(-1), moved_flat)
+            g, mid_layer = _grads_for_head(spec, dW[k], db[k], g_in[k], g_out[k], d_ll[k].reshape(-1))
             grads += g
-            d_rows[k] = delta[k, mid_layer].view(N, M, U).sum(dim=1)
+            d_rows[k] = delta[k, mid_layer].view(U // 4, N, M, 4).sum(dim=2).permute(1, 0, 2).reshape(N, U)
         return (None, None, None, None, d_rows, None, None, *grads)
 
 

@@ -505,6 +505,8 @@ def test_heads_backward_kernel_matches_autograd():
         moved, ll, act = ops.pf_heads_forward_train(plan.struct, states, eps, rows, 3)
         d_ll = torch.randn(plan.K, N, Mp, device=DEV, generator=g)
         delta = ops.pf_heads_backward(plan.struct, N, Mp, act, d_ll, 3)
+        dW, db, g_in, g_out = ops.pf_heads_weight_grads(act, delta, moved.reshape(-1, sd), d_ll.reshape(plan.K, -1))
+        act_r, delta_r = ops.rows_view(act), ops.rows_view(delta)  # chunk-major planes -> (K, L+1, P, 64)
         x = moved.reshape(-1, sd)
         for k, spec in enumerate(plan.heads):
             (in_lin, pre), (mid, post, out) = spec.state, spec.shared
@@ -538,10 +540,18 @@ def test_heads_backward_kernel_matches_autograd():
             (llk * d_ll[k].reshape(-1)).sum().backward()
             L = len(zs) - 1
             for i, a_ref in enumerate(acts):
-                assert_close(act[k, i].cpu(), a_ref.detach().cpu(), RTOL, msg=f"{name} head {k} activation {i}")
+                assert_close(act_r[k, i].cpu(), a_ref.detach().cpu(), RTOL, msg=f"{name} head {k} activation {i}")
             for l in range(L):
-                assert_close(delta[k, l].cpu(), zs[1 + l].grad.cpu(), 2e-4, msg=f"{name} head {k} delta {l}")
-            assert_close(delta[k, L].cpu(), zs[0].grad.cpu(), 2e-4, msg=f"{name} head {k} input-layer delta")
+                assert_close(delta_r[k, l].cpu(), zs[1 + l].grad.cpu(), 2e-4, msg=f"{name} head {k} delta {l}")
+                # weight gradient of layer l: delta_l^T a_l (fp32 reduction in mmf_pf_heads_weight_grads)
+                assert_close(dW[k, l].cpu(), (zs[1 + l].grad.t() @ acts[l].detach()).cpu(), 2e-4,
+                             msg=f"{name} head {k} dW {l}")
+            assert_close(delta_r[k, L].cpu(), zs[0].grad.cpu(), 2e-4, msg=f"{name} head {k} input-layer delta")
+            # thin layers at both ends and the biases (mmf_pf_heads_weight_grads, second kernel)
+            assert_close(g_in[k].cpu(), in_lin.weight.grad.cpu(), 2e-4, msg=f"{name} head {k} input-layer weight grad")
+            assert_close(db[k, L].cpu(), in_lin.bias.grad.cpu(), 2e-4, msg=f"{name} head {k} input-layer bias grad")
+            assert_close(g_out[k][None].cpu(), out.weight.grad.cpu(), 2e-4, msg=f"{name} head {k} output-layer weight grad")
+            assert_close(db[k, 0].cpu(), zs[1].grad.sum(0).cpu(), 2e-4, msg=f"{name} head {k} bias grad of layer 0")
 
 
 # ---- image encoder trunk: tcgen05 implicit-GEMM convolutions vs torch fp32 ---------------
