@@ -391,6 +391,180 @@ __global__ void __launch_bounds__(DW_THREADS) k_heads_dw(const float* __restrict
   if (tid < U) atomicAdd(db + ((size_t)head * planes_per_head + layer) * U + tid, colsum);
 }
 
+// ---- dW on the tensor cores -----------------------------------------------------------------------------------
+// dW = delta^T act is a (64 x rows) x (rows x 64) contraction with the ROWS as K.  Both operands are "MN-major" for
+// the MMA (the 64 features are the contiguous dimension), which tcgen05 takes directly from shared memory: a tile of
+// 64 rows is converted to bf16 hi/lo on the fly and written as 8(K) x 8(MN) core matrices,
+//   element (m, k) at (m / 8) * 1024 + (k / 8) * 128 + (k % 8) * 16 + (m % 8) * 2   [SBO = 1024, LBO = 128],
+// with the hi and lo halves STACKED along MN: A = [delta_hi ; delta_lo] (M = 128), B = [act_hi | act_lo] (N = 128),
+// so ONE M=128 N=128 K=16 MMA per 16 rows yields all four split products; the accumulator (128 lanes x 128 columns,
+// fp32, TMEM) lives across the CTA's whole row range and its quadrants are summed on the way out.
+// 0.92 ms (FFMA2 kernel above, 35 % of the fp32 FMA peak) -> HBM-bound.
+constexpr int DWT_ROWS = 64;                      // rows (K) per tile
+constexpr int DWT_OPERAND_B = 16 * 1024;          // [16 MN groups][8 K groups][8][8] bf16
+constexpr int DWT_THREADS = 256;
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {  // MN-major, no swizzle: LBO 128 B, SBO 1024 B
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_ss_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 8 fp32 -> 8 bf16 hi (rn) + 8 bf16 lo (rn of the exact remainder), 16 bytes each
+__device__ __forceinline__ void split8_rn(const float4& x0, const float4& x1, uint4& hi4, uint4& lo4) {
+  const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+    float rx, ry;
+    asm("{\n\t"
+        ".reg .b16 l, h, m1;\n\t"
+        "mov.b32 {l, h}, %2;\n\t"
+        "mov.b16 m1, 0xBF80;\n\t"
+        "fma.rn.f32.bf16 %0, l, m1, %3;\n\t"
+        "fma.rn.f32.bf16 %1, h, m1, %4;\n\t"
+        "}"
+        : "=f"(rx), "=f"(ry)
+        : "r"(hi[j]), "f"(v[2 * j]), "f"(v[2 * j + 1]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(ry), "f"(rx));
+  }
+  hi4 = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  lo4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__global__ void __launch_bounds__(DWT_THREADS, 1) k_heads_dw_tc(const float* __restrict__ act, const float* __restrict__ delta,
+                                                                float* __restrict__ dW, float* __restrict__ db, long long P,
+                                                                int planes_per_head, int L, int rows_per_cta) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // [buffer 0: A | B][buffer 1: A | B] + barriers
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 4 * DWT_OPERAND_B);  // [buffer]: the MMAs reading it are complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int layer = blockIdx.y, head = blockIdx.z;
+  const size_t plane = ((size_t)head * planes_per_head + layer) * (size_t)P * U;
+  const float* A = act + plane;
+  const float* D = delta + plane;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta;
+  const long long row1 = row0 + rows_per_cta < P ? row0 + rows_per_cta : P;
+  if (tid == 0) {
+    mbar_init(done, 1);
+    mbar_init(done + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // D fp32, A/B bf16, both MN-major (bits 15, 16), N = 128, M = 128
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+  // unit u = (column group of 8, row): this thread owns units tid and tid + 256 of every tile
+  float colsum[2][8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) colsum[q][j] = 0.0f;
+  uint32_t phase[2] = {0, 0};
+  long long t = 0;
+  for (long long r = row0; r < row1; r += DWT_ROWS, ++t) {
+    const int buf = (int)(t & 1);
+    uint8_t* sA = smem + buf * 2 * DWT_OPERAND_B;
+    uint8_t* sB = sA + DWT_OPERAND_B;
+    float4 dv[2][2], av[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int u = tid + q * DWT_THREADS;
+      const int m8 = u >> 6, rr = u & 63;
+      const bool ok = r + rr < row1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const size_t off = ((size_t)(2 * m8 + h) * P + (size_t)(r + rr)) * 4;
+        dv[q][h] = ok ? __ldg(reinterpret_cast<const float4*>(D + off)) : make_float4(0, 0, 0, 0);
+        av[q][h] = ok ? __ldg(reinterpret_cast<const float4*>(A + off)) : make_float4(0, 0, 0, 0);
+      }
+    }
+    if (t >= 2) {  // the MMAs of tile t - 2 read this buffer
+      mbar_wait(done + buf, phase[buf]);
+      phase[buf] ^= 1;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int u = tid + q * DWT_THREADS;
+      const int m8 = u >> 6, rr = u & 63;
+      const uint32_t core = (uint32_t)(rr >> 3) * 128 + (uint32_t)(rr & 7) * 16;
+      uint4 hi4, lo4;
+      split8_rn(dv[q][0], dv[q][1], hi4, lo4);
+      *reinterpret_cast<uint4*>(sA + (uint32_t)m8 * 1024 + core) = hi4;
+      *reinterpret_cast<uint4*>(sA + (uint32_t)(8 + m8) * 1024 + core) = lo4;
+      split8_rn(av[q][0], av[q][1], hi4, lo4);
+      *reinterpret_cast<uint4*>(sB + (uint32_t)m8 * 1024 + core) = hi4;
+      *reinterpret_cast<uint4*>(sB + (uint32_t)(8 + m8) * 1024 + core) = lo4;
+      colsum[q][0] += dv[q][0].x; colsum[q][1] += dv[q][0].y; colsum[q][2] += dv[q][0].z; colsum[q][3] += dv[q][0].w;
+      colsum[q][4] += dv[q][1].x; colsum[q][5] += dv[q][1].y; colsum[q][6] += dv[q][1].z; colsum[q][7] += dv[q][1].w;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+    __syncthreads();
+    if (warp == 0 && elect_one_sync()) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+#pragma unroll
+      for (int ks = 0; ks < DWT_ROWS / 16; ++ks)
+        mma_ss_f16(tmem_base, make_desc_mn(a_addr + ks * 256), make_desc_mn(b_addr + ks * 256), IDESC, (t > 0 || ks > 0) ? 1u : 0u);
+      tc_commit(done + buf);
+    }
+  }
+  // drain: the last one or two commits
+  for (int b = 0; b < 2; ++b) {
+    const long long used = (t + 1 - b) / 2;  // tiles that went through buffer b
+    if (used > 0) mbar_wait(done + b, phase[b]);
+  }
+  tc_fence_after();
+  if (t > 0 && warp < 4) {
+    // lanes 0..63: rows of delta_hi (quadrants hi*hi | hi*lo), lanes 64..127: rows of delta_lo (lo*hi | lo*lo)
+    const int lane_row = warp * 32 + (tid & 31);
+    const int j = lane_row & 63;
+    float* out = dW + ((size_t)head * L + layer) * U * U + (size_t)j * U;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) {
+      uint32_t x[16], y[16];
+      tmem_ld16(taddr + c, x);
+      tmem_ld16(taddr + 64 + c, y);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) atomicAdd(out + c + i, __uint_as_float(x[i]) + __uint_as_float(y[i]));
+    }
+  }
+  // bias gradient: reduce the per-thread column sums over the 32 rows of the warp, then one atomic per column
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int m8 = (tid + q * DWT_THREADS) >> 6;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      float v = colsum[q][jj];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) atomicAdd(db + ((size_t)head * planes_per_head + layer) * U + m8 * 8 + jj, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+}
+
 // Gradients of the two thin layers at the ends of a head, one pass over plane L of delta and act:
 //   g_in[k][j][d] = sum_p delta_in[p][j] * x[p][d]   (input layer weight, x = particle states)
 //   db[k][L][j]   = sum_p delta_in[p][j]             (input layer bias)
@@ -465,8 +639,30 @@ int launch_heads_dw(int K, int L, long long P, int sd, const float* act, const f
   rows_per_cta = ((rows_per_cta + DW_ROWS - 1) / DW_ROWS) * DW_ROWS;
   chunks = (P + rows_per_cta - 1) / rows_per_cta;
   dim3 grid((unsigned)chunks, (unsigned)L, (unsigned)K);
-  k_heads_dw<<<grid, DW_THREADS, 0, stream>>>(act, delta, dW, db, P, L + 1, L, (int)rows_per_cta);
-  MMF_LAUNCH_CHECK("k_heads_dw");
+  int variant = 1;  // MMF_DW_VARIANT: 1 = tcgen05 (default), 0 = fp32 FFMA2 on the CUDA cores
+  if (const char* env = getenv("MMF_DW_VARIANT")) variant = atoi(env);
+  if (variant == 1) {
+    const size_t smem = 4 * DWT_OPERAND_B + 64;
+    static thread_local int configured_dev = -1;
+    static thread_local size_t window = 0;
+    if (configured_dev != dev) {
+      int rc = opt_in_shared_memory(k_heads_dw_tc, &window);
+      if (rc) return rc;
+      configured_dev = dev;
+    }
+    MMF_REQUIRE(smem <= window, "heads_weight_grads needs %zu B of shared memory (window %zu B)", smem, window);
+    // one CTA per SM-slot: 3 CTAs of 64 KB fit an SM
+    long long tc_chunks = ((long long)sms * 3 + (long long)K * L - 1) / ((long long)K * L);
+    long long tc_rows = (P + tc_chunks - 1) / tc_chunks;
+    tc_rows = ((tc_rows + DWT_ROWS - 1) / DWT_ROWS) * DWT_ROWS;
+    tc_chunks = (P + tc_rows - 1) / tc_rows;
+    k_heads_dw_tc<<<dim3((unsigned)tc_chunks, (unsigned)L, (unsigned)K), DWT_THREADS, smem, stream>>>(act, delta, dW, db, P,
+                                                                                                   L + 1, L, (int)tc_rows);
+    MMF_LAUNCH_CHECK("k_heads_dw_tc");
+  } else {
+    k_heads_dw<<<grid, DW_THREADS, 0, stream>>>(act, delta, dW, db, P, L + 1, L, (int)rows_per_cta);
+    MMF_LAUNCH_CHECK("k_heads_dw");
+  }
   long long edge_chunks = ((long long)sms * 4 + K - 1) / K;
   long long edge_rows = (P + edge_chunks - 1) / edge_chunks;
   edge_rows = ((edge_rows + 15) / 16) * 16;
