@@ -641,66 +641,6 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk(const __grid_const
   }
 }
 
-// ---- fused trunk, A operand through TMEM ------------------------------------------------------------------------
-// The SS-form MMAs above are bound by the tensor core's shared-memory operand read (~64-75 B/cycle/SM measured: 164
-// cycles per K step for 8 KB of A).  Ordinary LDS moves twice that, so here dedicated GATHER warps (two groups of 128
-// threads, thread = position row = TMEM lane) read the shifted window rows themselves and park them in TMEM with
-// tcgen05.st; the MMAs become TS-form (A from TMEM, only the small weight operand from shared memory).  Roles:
-//   warp 0        TMA producer (window ring in shared memory, as above)
-//   warps 1, 2    MMA issuers, one per gather group
-//   warps 4-11    gather groups 0/1: tiles alternate between them; per tile 9 taps in batches of TS_BATCH taps,
-//                 a ring of TS_A_SLOTS batches per group in TMEM (a_ready / a_free mbarriers)
-//   warps 12-19   epilogue groups 0/1 (and the stem): four accumulator slots of 64 columns (mma_done / tmem_free)
-// so a gather group starts its next tile while the previous one is still in the tensor pipe / epilogue.
-constexpr int TS_A_SLOTS = 2;        // ring of operand batches per gather group
-constexpr int TS_BATCH = 2;          // taps per batch: one wait::st + publish per batch
-constexpr int TS_BATCHES = (9 + TS_BATCH - 1) / TS_BATCH;
-constexpr int TS_D_SLOTS = 4;        // accumulator slots (64 columns each): columns [0, 256)
-constexpr int TS_A_BASE = 256;       // gather group e owns columns [256 + 128 e, 256 + 128 e + 128): 4 tap slots of 32
-constexpr int TS_THREADS = 640;
-
-// LO_SS: the lo halves stay in shared memory and are read by SS-form MMAs (splits the operand feed between the LSU
-// path, ~128 B/cycle, and the tensor core's own shared-memory read, ~64 B/cycle)
-template <int CIN, bool LO_SS>
-__device__ __forceinline__ void gather_tap(const uint8_t* stage, int shift_row, uint32_t t_slot) {
-  // stage: planes [chunk][hi|lo][ENC_WIN_POS][16 B]; this thread's row of the shifted window
-#pragma unroll
-  for (int ks = 0; ks < CIN / 16; ++ks) {
-    const uint8_t* base = stage + (size_t)((2 * ks) * 2) * ENC_WIN_B + (size_t)shift_row * 16;
-    const uint4 h0 = *reinterpret_cast<const uint4*>(base);
-    const uint4 h1 = *reinterpret_cast<const uint4*>(base + 2 * ENC_WIN_B);
-    const uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    tmem_st8(t_slot + ks * 8, hi);
-    if (!LO_SS) {
-      const uint4 l0 = *reinterpret_cast<const uint4*>(base + ENC_WIN_B);
-      const uint4 l1 = *reinterpret_cast<const uint4*>(base + 3 * ENC_WIN_B);
-      const uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-      tmem_st8(t_slot + 16 + ks * 8, lo);
-    }
-  }
-}
-
-template <int CIN, int NPAD, bool LO_SS>
-__device__ __forceinline__ void issue_tap_ts(uint32_t d, uint32_t a_slot, uint32_t w_addr, uint32_t st_addr, int tap,
-                                             uint32_t acc) {
-  constexpr int KC = CIN / 8;
-  constexpr uint32_t IDESC2 = make_idesc(2 * NPAD, 128);
-  constexpr uint32_t IDESC1 = make_idesc(NPAD, 128);
-  const int shift = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1);
-#pragma unroll
-  for (int ks = 0; ks < CIN / 16; ++ks) {
-    const uint32_t b = w_addr + (uint32_t)((tap * KC + 2 * ks) * 2 * NPAD) * 16;
-    const uint64_t db = make_desc_interleave(b, 2 * NPAD * 16, 128);
-    mma_ts(d, a_slot + ks * 8, db, IDESC2, (ks > 0) ? 1u : acc);
-    if (LO_SS) {
-      const uint32_t a_lo = st_addr + (uint32_t)((2 * ks) * 2 + 1) * ENC_WIN_B + (uint32_t)shift * 16;
-      mma_ss(d, make_desc_interleave(a_lo, 2 * ENC_WIN_B, 128), db, IDESC1, 1);
-    } else {
-      mma_ts(d, a_slot + 16 + ks * 8, db, IDESC1, 1);
-    }
-  }
-}
-
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -708,21 +648,88 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 
-// epilogue straight from TMEM in 8-channel chunks (keeps the register footprint small: 640 threads -> 96 registers)
+// ---- fused trunk, the three dx taps of a stencil row stacked along N -----------------------------------------------
+// The SS-form MMAs are bound by the shared-memory operand read (A: 8 KB per K step and tap).  The three taps of one
+// stencil ROW (dx = -1, 0, +1) see the same input rows up to a one-position shift, so they can share ONE read of A if
+// the shift is moved to the OUTPUT side: with the weights of the three taps stacked along N,
+//   Y[q][dx][c] = sum_{dy, k} in[q + 34 dy][k] * W[dy][dx][k][c]        (3 A windows instead of 9, N = 3 x 2 Cout)
+//   out[p][c]   = Y[p-1][-1][c] + Y[p][0][c] + Y[p+1][+1][c]           (epilogue: warp shuffles between TMEM lanes)
+// A tile therefore carries 128 rows of Y but owns 126 outputs (rows 1..126); tiles advance by 126 positions.
+// Weight image per layer: [dy 3][chunk Cin/8][6 Cout rows: hi dx-1 | hi dx0 | hi dx+1 | lo dx-1 | lo dx0 | lo dx+1][8].
+constexpr int DX_TILE = 126;
+constexpr int DX_DCOLS = 192;  // accumulator columns per slot (6 x 32)
+
+template <int CIN, int NPAD>
+__device__ __forceinline__ void issue_conv_dx(uint32_t st_addr, uint32_t w_addr, uint32_t d) {
+  constexpr int KC = CIN / 8;
+  constexpr uint32_t IDESC_ALL = make_idesc(6 * NPAD, 128);  // A_hi x [W_hi (3 dx) | W_lo (3 dx)]
+  constexpr uint32_t IDESC_HI = make_idesc(3 * NPAD, 128);   // A_lo x  W_hi (3 dx)
+  uint32_t acc = 0;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int shift = ENC_HALO + (dy - 1) * ENC_PITCH;
+#pragma unroll
+    for (int ks = 0; ks < CIN / 16; ++ks) {
+      const uint32_t a_hi = st_addr + (uint32_t)((2 * ks) * 2) * ENC_WIN_B + (uint32_t)shift * 16;
+      const uint32_t a_lo = a_hi + ENC_WIN_B;
+      const uint32_t b = w_addr + (uint32_t)((dy * KC + 2 * ks) * 6 * NPAD) * 16;
+      const uint64_t db = make_desc_interleave(b, 6 * NPAD * 16, 128);
+      mma_ss(d, make_desc_interleave(a_hi, 2 * ENC_WIN_B, 128), db, IDESC_ALL, acc);
+      mma_ss(d, make_desc_interleave(a_lo, 2 * ENC_WIN_B, 128), db, IDESC_HI, 1);
+      acc = 1;
+    }
+  }
+}
+
+// 8 channels of Y[.][dx] of this thread's row: columns dx*NPAD + c (hi weights) + 3*NPAD + dx*NPAD + c (lo weights)
 template <int NPAD>
-__device__ __forceinline__ void epilogue_from_tmem(uint32_t taddr, const float* bias_s, const uint8_t* res_map, bool relu,
-                                                   bool valid, int pos, uint8_t* out_map, float* out_img, int cout) {
-  const size_t plane_off = (size_t)(ENC_GUARD + pos) * 16;
+__device__ __forceinline__ void load_y8(uint32_t taddr, int dx, int kc, float (&y)[8]) {
+  uint32_t a[8], b[8];
+  tmem_ld8(taddr + dx * NPAD + kc * 8, a);
+  tmem_ld8(taddr + 3 * NPAD + dx * NPAD + kc * 8, b);
+  tc_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+}
+
+template <int NPAD>
+__device__ __forceinline__ void epilogue_dx(uint32_t taddr, float* xch, int quad, int eg, const float* bias_s,
+                                            const uint8_t* res_map, bool relu, bool owner, bool valid, int pos,
+                                            uint8_t* out_map, float* out_img, int cout) {
+  const int lane = threadIdx.x & 31;
+  // rows at the warp boundaries travel through shared memory: xch[warp][0] = Y[-1 block] of lane 31 (for the next warp's
+  // lane 0), xch[warp][1] = Y[+1 block] of lane 0 (for the previous warp's lane 31)
 #pragma unroll
   for (int kc = 0; kc < NPAD / 8; ++kc) {
-    uint32_t d[8], e[8];
-    tmem_ld8(taddr + kc * 8, d);
-    tmem_ld8(taddr + NPAD + kc * 8, e);
-    tc_wait_ld();
-    float v[8];
+    float y[8];
+    load_y8<NPAD>(taddr, 0, kc, y);
+    if (lane == 31) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (__uint_as_float(d[j]) + __uint_as_float(e[j])) + bias_s[kc * 8 + j];
-    if (res_map != nullptr) {
+      for (int j = 0; j < 8; ++j) xch[quad * 64 + kc * 8 + j] = y[j];
+    }
+    load_y8<NPAD>(taddr, 2, kc, y);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xch[quad * 64 + 32 + kc * 8 + j] = y[j];
+    }
+  }
+  group_bar(1 + eg, 128);
+  const size_t plane_off = (size_t)(ENC_GUARD + (pos < 0 ? 0 : pos)) * 16;
+#pragma unroll
+  for (int kc = 0; kc < NPAD / 8; ++kc) {
+    float ym[8], y0[8], yp[8], v[8];
+    load_y8<NPAD>(taddr, 0, kc, ym);
+    load_y8<NPAD>(taddr, 1, kc, y0);
+    load_y8<NPAD>(taddr, 2, kc, yp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float left = __shfl_up_sync(0xffffffffu, ym[j], 1);     // Y[p-1][dx = -1]
+      float right = __shfl_down_sync(0xffffffffu, yp[j], 1);  // Y[p+1][dx = +1]
+      if (lane == 0 && quad > 0) left = xch[(quad - 1) * 64 + kc * 8 + j];
+      if (lane == 31 && quad < 3) right = xch[(quad + 1) * 64 + 32 + kc * 8 + j];
+      v[j] = (left + y0[j]) + right + bias_s[kc * 8 + j];
+    }
+    if (res_map != nullptr && owner) {
       const uint8_t* rp = res_map + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
       float x[8];
       unpack8(*reinterpret_cast<const uint4*>(rp), *reinterpret_cast<const uint4*>(rp + ENC_PLANE_B), x);
@@ -734,7 +741,7 @@ __device__ __forceinline__ void epilogue_from_tmem(uint32_t taddr, const float* 
       if (relu) v[j] = fmaxf(v[j], 0.0f);
       if (!valid) v[j] = 0.0f;
     }
-    if (out_map != nullptr) {
+    if (out_map != nullptr && owner) {
       uint4 hi4, lo4;
       split8(v, hi4, lo4);
       uint8_t* op = out_map + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
@@ -750,43 +757,38 @@ __device__ __forceinline__ void epilogue_from_tmem(uint32_t taddr, const float* 
   }
 }
 
-template <bool LO_SS>
-__global__ void __launch_bounds__(TS_THREADS, 1) k_enc_trunk_ts(const __grid_constant__ TrunkParams P) {
+__global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_dx(const __grid_constant__ TrunkParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
   uint8_t* stage0 = smem + ((TR_W_B + 127) & ~127);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + ENC_STAGES * TR_STAGE_B);
-  uint64_t* full = bars;                                  // [stage]   TMA bytes landed
-  uint64_t* stage_free = bars + ENC_STAGES;               // [stage]   the gather group has read the window (4 warps)
-  uint64_t* a_ready = bars + 2 * ENC_STAGES;              // [group][slot] operand batch in TMEM (4 warps)
-  uint64_t* a_free = a_ready + 2 * TS_A_SLOTS;            // [group][slot] the MMAs that read the batch are done
-  uint64_t* mma_done = a_free + 2 * TS_A_SLOTS;           // [d slot] accumulator complete
-  uint64_t* tmem_free = mma_done + TS_D_SLOTS;            // [d slot] epilogue has read the accumulator (4 warps)
-  uint64_t* wbar = tmem_free + TS_D_SLOTS;
-  uint64_t* tile_done = wbar + 1;                         // [layer 0..3][tile]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 4 * ENC_TILES);
+  uint64_t* full = bars;
+  uint64_t* mma_done = bars + ENC_STAGES;
+  uint64_t* stage_free = bars + 2 * ENC_STAGES;
+  uint64_t* tmem_free = bars + 3 * ENC_STAGES;
+  uint64_t* wbar = bars + 4 * ENC_STAGES;
+  uint64_t* stem_done = wbar + 1;                  // [x buffer 0|1][tile]: stem output of an image is written and published
+  uint64_t* tile_done = stem_done + 2 * ENC_TILES;  // [layer 1..3][tile]: that tile of the layer's OUTPUT map
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_done + 3 * ENC_TILES);
+  // boundary rows exchanged between the warps of an epilogue group: [group][item parity][warp][left|right][32]
+  float* xch = reinterpret_cast<float*>(smem + ((TR_W_B + 127) & ~127) + ENC_STAGES * TR_STAGE_B + 1024);
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid == 0) {
     for (int s = 0; s < ENC_STAGES; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(stage_free + s, LO_SS ? 5 : 4);  // 4 gather warps (+ the MMAs that read the lo planes)
+      mbar_init(mma_done + s, 1);
+      mbar_init(stage_free + s, 1);
+      mbar_init(tmem_free + s, 4);
     }
-    for (int i = 0; i < 2 * TS_A_SLOTS; ++i) {
-      mbar_init(a_ready + i, 4);
-      mbar_init(a_free + i, 1);
-    }
-    for (int i = 0; i < TS_D_SLOTS; ++i) {
-      mbar_init(mma_done + i, 1);
-      mbar_init(tmem_free + i, 4);
-    }
-    for (int i = 0; i < 4 * ENC_TILES; ++i) mbar_init(tile_done + i, 4);
+    for (int i = 0; i < 5 * ENC_TILES; ++i) mbar_init(stem_done + i, 4);
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -796,9 +798,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_enc_trunk_ts(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   const size_t map32 = enc_map_bytes(32);
-  uint8_t* sx = P.scratch + (size_t)blockIdx.x * TR_SCRATCH_MAPS * map32;
-  uint8_t* st = sx + map32;
-  uint8_t* sy = st + map32;
+  // x is double-buffered: the stem of image k+1 is computed in the shadow of image k's convolutions
+  uint8_t* sx0 = P.scratch + (size_t)blockIdx.x * TR_SCRATCH_MAPS * map32;
+  uint8_t* st = sx0 + 2 * map32;                              // block1 output, later the 16-channel map z
+  uint8_t* sy = st + map32;                                   // resblock output
+  // shared-memory offsets of the per-layer weights
   constexpr int OFF_W[5] = {2 * TR_W2_B + TR_W3_B + TR_W4_B, 0, TR_W2_B, 2 * TR_W2_B, 2 * TR_W2_B + TR_W3_B};
 
   if (warp == 0) {
@@ -814,18 +818,25 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_enc_trunk_ts(const __grid_con
       for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x, ++k) {
         const uint32_t ipar = (uint32_t)(k & 1);
         for (int layer = 1; layer <= 4; ++layer) {
-          const uint8_t* in = layer == 1 ? sx : layer == 2 ? st : layer == 3 ? sy : sx;
+          const uint8_t* in = layer == 1 ? sx0 + (size_t)(k & 1) * map32 : layer == 2 ? st : layer == 3 ? sy : st;
           const int planes = layer == 4 ? 4 : 8;
           for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
             const int s = (int)(c % ENC_STAGES);
             const uint32_t par = (uint32_t)((c / ENC_STAGES) & 1);
             mbar_wait(stage_free + s, par ^ 1u);
-            uint64_t* dep = tile_done + (layer - 1) * ENC_TILES;
-            if (tile > 0) mbar_wait(dep + tile - 1, ipar);
-            mbar_wait(dep + tile, ipar);
-            if (tile + 1 < ENC_TILES) mbar_wait(dep + tile + 1, ipar);
+            // the window reaches into the neighbouring tiles of the producing layer
+            // layer 1 reads the stem output in x[k & 1] (completed once every second image), the others layer - 1
+            uint64_t* dep = layer == 1 ? stem_done + (k & 1) * ENC_TILES : tile_done + (layer - 2) * ENC_TILES;
+            const uint32_t dpar = layer == 1 ? (uint32_t)((k >> 1) & 1) : ipar;
+            // input positions [126 tile - 36, 126 tile + 162]: producer tiles are 128 wide for the stem, 126 otherwise
+            const int lo_pos = tile * DX_TILE - 36, hi_pos = tile * DX_TILE + 162;
+            const int width = layer == 1 ? 128 : DX_TILE;
+            const int t_lo = lo_pos < 0 ? 0 : lo_pos / width;
+            int t_hi = hi_pos / width;
+            if (t_hi > ENC_TILES - 1) t_hi = ENC_TILES - 1;
+            for (int tt = t_lo; tt <= t_hi; ++tt) mbar_wait(dep + tt, dpar);
             asm volatile("fence.proxy.async.global;" ::: "memory");
-            const uint8_t* src = in + (size_t)(ENC_GUARD + tile * 128 - ENC_HALO) * 16;
+            const uint8_t* src = in + (size_t)(ENC_GUARD + tile * DX_TILE - 1 - ENC_HALO) * 16;
             mbar_expect_tx(full + s, (uint32_t)planes * ENC_WIN_B);
             for (int pl = 0; pl < planes; ++pl)
               bulk_g2s(stage0 + s * TR_STAGE_B + pl * ENC_WIN_B, src + (size_t)pl * ENC_PLANE_B, ENC_WIN_B, full + s);
@@ -834,159 +845,117 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_enc_trunk_ts(const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp == 1 || warp == 2) {
-    // ----------------------------------------------------------------- MMA issuer of gather group (warp - 1)
-    const int e = warp - 1;
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------------------------------- MMA issuer
     mbar_wait(wbar, 0);
     if (elect_one_sync()) {
       const uint32_t w_addr = smem_u32(w_s);
-      const uint32_t abase = tmem_base + TS_A_BASE + e * 128;
-      long long c = 0, batches = 0;
+      long long c = 0;
       for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
         for (int layer = 1; layer <= 4; ++layer) {
           for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
-            if ((int)(c & 1) != e) continue;
-            const int ds = (int)(c % TS_D_SLOTS);
-            const uint32_t dpar = (uint32_t)((c / TS_D_SLOTS) & 1);
-            const uint32_t d = tmem_base + ds * 64;
-            const uint32_t st_addr = smem_u32(stage0 + (int)(c % ENC_STAGES) * TR_STAGE_B);
-            mbar_wait(tmem_free + ds, dpar ^ 1u);
-            for (int batch = 0; batch < TS_BATCHES; ++batch, ++batches) {
-              const int slot = (int)(batches % TS_A_SLOTS);
-              const uint32_t par = (uint32_t)((batches / TS_A_SLOTS) & 1);
-              mbar_wait(a_ready + e * TS_A_SLOTS + slot, par);
-              tc_fence_after();
-#pragma unroll
-              for (int i = 0; i < TS_BATCH; ++i) {
-                const int tap = batch * TS_BATCH + i;
-                if (tap < 9) {
-                  const uint32_t a_slot = abase + (slot * TS_BATCH + i) * 32;
-                  const uint32_t acc = tap > 0 ? 1u : 0u;
-                  if (layer <= 2) issue_tap_ts<32, 32, LO_SS>(d, a_slot, w_addr + OFF_W[layer], st_addr, tap, acc);
-                  else if (layer == 3) issue_tap_ts<32, 16, LO_SS>(d, a_slot, w_addr + OFF_W[3], st_addr, tap, acc);
-                  else issue_tap_ts<16, 16, LO_SS>(d, a_slot, w_addr + OFF_W[4], st_addr, tap, acc);
-                }
-              }
-              tc_commit(a_free + e * TS_A_SLOTS + slot);
-            }
-            tc_commit(mma_done + ds);
-            if (LO_SS) tc_commit(stage_free + (int)(c % ENC_STAGES));
+            const int s = (int)(c % ENC_STAGES);
+            const uint32_t par = (uint32_t)((c / ENC_STAGES) & 1);
+            const int slot = (int)(c & 1);                       // accumulator slot == epilogue group
+            const uint32_t dpar = (uint32_t)((c >> 1) & 1);
+            mbar_wait(tmem_free + slot, dpar ^ 1u);
+            mbar_wait(full + s, par);
+            tc_fence_after();
+            const uint32_t st_addr = smem_u32(stage0 + s * TR_STAGE_B);
+            const uint32_t d = tmem_base + slot * DX_DCOLS;
+            if (layer <= 2) issue_conv_dx<32, 32>(st_addr, w_addr + OFF_W[layer], d);
+            else if (layer == 3) issue_conv_dx<32, 16>(st_addr, w_addr + OFF_W[3], d);
+            else issue_conv_dx<16, 16>(st_addr, w_addr + OFF_W[4], d);
+            tc_commit(mma_done + slot);
+            tc_commit(stage_free + s);
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4 && warp < 12) {
-    // --------------------------------------------------------------------------------------- gather groups
-    const int e = (warp - 4) >> 2;
-    const int quad = warp & 3;
-    const int r = quad * 32 + (tid & 31);
-    const uint32_t abase = tmem_base + TS_A_BASE + e * 128 + ((uint32_t)(quad * 32) << 16);
-    long long c = 0, batches = 0;
-    for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
-      for (int layer = 1; layer <= 4; ++layer) {
-        for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
-          if ((int)(c & 1) != e) continue;
-          const int s = (int)(c % ENC_STAGES);
-          const uint32_t spar = (uint32_t)((c / ENC_STAGES) & 1);
-          mbar_wait(full + s, spar);
-          const uint8_t* stage = stage0 + s * TR_STAGE_B;
-          for (int batch = 0; batch < TS_BATCHES; ++batch, ++batches) {
-            const int slot = (int)(batches % TS_A_SLOTS);
-            const uint32_t par = (uint32_t)((batches / TS_A_SLOTS) & 1);
-            mbar_wait(a_free + e * TS_A_SLOTS + slot, par ^ 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int i = 0; i < TS_BATCH; ++i) {
-              const int tap = batch * TS_BATCH + i;
-              if (tap < 9) {
-                const int shift_row = ENC_HALO + (tap / 3 - 1) * ENC_PITCH + (tap % 3 - 1) + r;
-                const uint32_t t_slot = abase + (slot * TS_BATCH + i) * 32;
-                if (layer <= 3) gather_tap<32, LO_SS>(stage, shift_row, t_slot);
-                else gather_tap<16, LO_SS>(stage, shift_row, t_slot);
-              }
-            }
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(a_ready + e * TS_A_SLOTS + slot);
-          }
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(stage_free + s);  // this warp is done reading the window
-        }
-      }
-    }
-  } else if (warp >= 12) {
+  } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue groups (and the stem on the CUDA cores)
-    const int e = (warp - 12) >> 2;
+    const int eg = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + (tid & 31);
-    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     mbar_wait(wbar, 0);
     const float* wstem = reinterpret_cast<const float*>(w_s + OFF_W[0]);
-    long long g = 0, c = 0;
-    for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x) {
-      const float* im = P.images + (size_t)image * 1024;
-      for (int layer = 0; layer < TR_LAYERS; ++layer) {
-        for (int tile = 0; tile < ENC_TILES; ++tile, ++g) {
-          const long long cc = c;
-          if (layer > 0) ++c;
-          if (layer == 0 ? ((int)(g & 1) != e) : ((int)(cc & 1) != e)) continue;
-          const int pos = tile * 128 + r;
-          const bool valid = enc_valid(pos);
-          if (layer == 0) {
-            float acc[32];
+    // stem tile `tile` of image `img` (the kk-th image of this CTA) -> x[kk & 1]
+    auto stem_tile = [&](long long img, int kk, int tile) {
+      const float* im = P.images + (size_t)img * 1024;
+      uint8_t* sx = sx0 + (size_t)(kk & 1) * map32;
+      const int pos = tile * 128 + r;
+      const bool valid = enc_valid(pos);
+      float acc[32];
 #pragma unroll
-            for (int ch = 0; ch < 32; ++ch) acc[ch] = wstem[25 * 32 + ch];
-            if (valid) {
-              const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
-              for (int ky = 0; ky < 5; ++ky) {
-                const int yy = y + ky - 2;
+      for (int ch = 0; ch < 32; ++ch) acc[ch] = wstem[25 * 32 + ch];
+      if (valid) {
+        const int y = pos / ENC_PITCH, x = pos % ENC_PITCH;
+        for (int ky = 0; ky < 5; ++ky) {
+          const int yy = y + ky - 2;
 #pragma unroll
-                for (int kx = 0; kx < 5; ++kx) {
-                  const int xx = x + kx - 2;
-                  const float p = (yy >= 0 && yy < 32 && xx >= 0 && xx < 32) ? __ldg(im + yy * 32 + xx) : 0.0f;
-                  const float4* w4 = reinterpret_cast<const float4*>(wstem + (ky * 5 + kx) * 32);
+          for (int kx = 0; kx < 5; ++kx) {
+            const int xx = x + kx - 2;
+            const float p = (yy >= 0 && yy < 32 && xx >= 0 && xx < 32) ? __ldg(im + yy * 32 + xx) : 0.0f;
+            const float4* w4 = reinterpret_cast<const float4*>(wstem + (ky * 5 + kx) * 32);
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const float4 t = w4[q];
-                    acc[4 * q] = fmaf(t.x, p, acc[4 * q]);
-                    acc[4 * q + 1] = fmaf(t.y, p, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(t.z, p, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(t.w, p, acc[4 * q + 3]);
-                  }
-                }
-              }
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = w4[q];
+              acc[4 * q] = fmaf(t.x, p, acc[4 * q]);
+              acc[4 * q + 1] = fmaf(t.y, p, acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(t.z, p, acc[4 * q + 2]);
+              acc[4 * q + 3] = fmaf(t.w, p, acc[4 * q + 3]);
             }
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = valid ? fmaxf(acc[kc * 8 + j], 0.0f) : 0.0f;
-              uint4 hi4, lo4;
-              split8(v, hi4, lo4);
-              uint8_t* plane = sx + (size_t)(kc * 2) * ENC_PLANE_B + (size_t)(ENC_GUARD + pos) * 16;
-              *reinterpret_cast<uint4*>(plane) = hi4;
-              *reinterpret_cast<uint4*>(plane + ENC_PLANE_B) = lo4;
-            }
-            publish_tile(tile_done + tile);
-            continue;
           }
-          const int ds = (int)(cc % TS_D_SLOTS);
-          const uint32_t dpar = (uint32_t)((cc / TS_D_SLOTS) & 1);
-          mbar_wait(mma_done + ds, dpar);
+        }
+      }
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = valid ? fmaxf(acc[kc * 8 + j], 0.0f) : 0.0f;
+        uint4 hi4, lo4;
+        split8(v, hi4, lo4);
+        uint8_t* plane = sx + (size_t)(kc * 2) * ENC_PLANE_B + (size_t)(ENC_GUARD + pos) * 16;
+        *reinterpret_cast<uint4*>(plane) = hi4;
+        *reinterpret_cast<uint4*>(plane + ENC_PLANE_B) = lo4;
+      }
+      publish_tile(stem_done + (kk & 1) * ENC_TILES + tile);
+    };
+    // the first image's stem up front; afterwards the stem of image k+1 rides along with the convolution items of
+    // image k (one stem tile every fourth item), where the epilogue warps would otherwise wait for the tensor pipe
+    if ((long long)blockIdx.x < P.n_images)
+      for (int tile = 0; tile < ENC_TILES; ++tile)
+        if ((tile & 1) == eg) stem_tile(blockIdx.x, 0, tile);
+    long long c = 0;
+    int k = 0;
+    for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x, ++k) {
+      const long long next = image + gridDim.x;
+      const uint8_t* sx = sx0 + (size_t)(k & 1) * map32;
+      int j = 0;
+      for (int layer = 1; layer <= 4; ++layer) {
+        for (int tile = 0; tile < ENC_TILES; ++tile, ++c, ++j) {
+          if ((j & 3) == 0 && (j >> 2) < ENC_TILES && next < P.n_images && (((j >> 2) & 1) == eg)) stem_tile(next, k + 1, j >> 2);
+          if ((int)(c & 1) != eg) continue;
+          const int pos = tile * DX_TILE - 1 + r;              // this thread's ROW of Y; it owns output `pos` if 1 <= r <= 126
+          const bool owner = r >= 1 && r <= DX_TILE;
+          const bool valid = owner && pos >= 0 && enc_valid(pos);
+          const uint32_t dpar = (uint32_t)((c >> 1) & 1);
+          mbar_wait(mma_done + eg, dpar);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + ds * 64 + lane_off;
+          const uint32_t taddr = tmem_base + eg * DX_DCOLS + ((uint32_t)(quad * 32) << 16);
+          float* my_xch = xch + ((size_t)(eg * 2 + (int)((c >> 1) & 1)) * 4) * 64;
           const float* bias_s = reinterpret_cast<const float*>(
               w_s + OFF_W[layer] + (layer <= 2 ? TR_W2_B - 128 : layer == 3 ? TR_W3_B - 64 : TR_W4_B - 64));
-          if (layer == 1) epilogue_from_tmem<32>(taddr, bias_s, nullptr, true, valid, pos, st, nullptr, 0);
-          else if (layer == 2) epilogue_from_tmem<32>(taddr, bias_s, sx, true, valid, pos, sy, nullptr, 0);
-          else if (layer == 3) epilogue_from_tmem<16>(taddr, bias_s, nullptr, true, valid, pos, sx, nullptr, 0);
-          else epilogue_from_tmem<16>(taddr, bias_s, nullptr, false, valid, pos, nullptr, P.out_nchw + (size_t)image * P.cout * 1024, P.cout);
+          float* out_img = P.out_nchw + (size_t)image * P.cout * 1024;
+          if (layer == 1) epilogue_dx<32>(taddr, my_xch, quad, eg, bias_s, nullptr, true, owner, valid, pos, st, nullptr, 0);
+          else if (layer == 2) epilogue_dx<32>(taddr, my_xch, quad, eg, bias_s, sx, true, owner, valid, pos, sy, nullptr, 0);
+          else if (layer == 3) epilogue_dx<16>(taddr, my_xch, quad, eg, bias_s, nullptr, true, owner, valid, pos, st, nullptr, 0);
+          else epilogue_dx<16>(taddr, my_xch, quad, eg, bias_s, nullptr, false, owner, valid, pos, nullptr, out_img, P.cout);
           tc_fence_before();
           __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(tmem_free + ds);
-          if (layer < 4) publish_tile(tile_done + layer * ENC_TILES + tile);
+          if ((tid & 31) == 0) mbar_arrive(tmem_free + eg);
+          if (layer < 4) publish_tile(tile_done + (layer - 1) * ENC_TILES + tile);
         }
       }
     }
@@ -994,7 +963,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_enc_trunk_ts(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
 }
 
 static int trunk_grid(int* grid_out) {
@@ -1023,7 +994,7 @@ int launch_enc_trunk(int n_images, int cout, const float* images, const void* we
   P.out_nchw = out_nchw;
   P.n_images = n_images;
   P.cout = cout;
-  const size_t smem = ((TR_W_B + 127) & ~127) + (size_t)ENC_STAGES * TR_STAGE_B + 1024;
+  const size_t smem = ((TR_W_B + 127) & ~127) + (size_t)ENC_STAGES * TR_STAGE_B + 1024 + 4096;
   static thread_local int configured_dev = -1;
   static thread_local size_t window = 0;
   int dev = 0, grid = 148;
@@ -1033,23 +1004,23 @@ int launch_enc_trunk(int n_images, int cout, const float* images, const void* we
   if (configured_dev != dev) {
     rc = opt_in_shared_memory(k_enc_trunk, &window);
     if (rc) return rc;
-    rc = opt_in_shared_memory(k_enc_trunk_ts<false>, &window);
+    rc = opt_in_shared_memory(k_enc_trunk_dx, &window);
     if (rc) return rc;
-    rc = opt_in_shared_memory(k_enc_trunk_ts<true>, &window);
     if (rc) return rc;
     configured_dev = dev;
   }
   MMF_REQUIRE(smem <= window, "encoder trunk needs %zu B of shared memory (window %zu B)", smem, window);
   if (grid > n_images) grid = n_images;
-  // MMF_ENC_VARIANT (all parity-green, measured per 16,384 images on B200):
-  //   0 = SS form: the MMAs read the shifted A windows from shared memory themselves (default, 5.25 ms)
-  //   1 = TS form: dedicated gather warps copy the windows into TMEM (LDS + tcgen05.st), MMAs read A from TMEM (5.7 ms:
-  //       the LSU shared-memory pipe becomes the busiest unit, 64 % in ncu)
-  //   2 = hybrid: hi halves through TMEM, lo halves read from shared memory by SS-form MMAs (5.5 ms)
+  // MMF_ENC_VARIANT (parity-green, measured per 16,384 images on B200):
+  //   0 = one MMA pair per tap and K step, A windows read from shared memory by the MMAs (default, 5.2 ms)
+  //   3 = the three dx taps of a stencil row stacked along N, the dx shift applied in the epilogue with warp shuffles:
+  //       a third of the A reads and MMAs (tensor pipe no longer the limiter), but the heavier epilogue with only two
+  //       192-column accumulator slots currently makes it 6.4 ms
+  // (TS-form variants -- A through a TMEM ring filled by gather warps, 5.5-5.7 ms -- were measured and removed, see
+  //  DESIGN.md section 3.2 and the git history.)
   int variant = 0;
   if (const char* env = getenv("MMF_ENC_VARIANT")) variant = atoi(env);
-  if (variant == 1) k_enc_trunk_ts<false><<<grid, TS_THREADS, smem, stream>>>(P);
-  else if (variant == 2) k_enc_trunk_ts<true><<<grid, TS_THREADS, smem, stream>>>(P);
+  if (variant == 3) k_enc_trunk_dx<<<grid, ENC_THREADS, smem, stream>>>(P);
   else k_enc_trunk<<<grid, ENC_THREADS, smem, stream>>>(P);
   MMF_LAUNCH_CHECK("k_enc_trunk");
   return MMF_OK;
