@@ -655,15 +655,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 //   Y[q][dx][c] = sum_{dy, k} in[q + 34 dy][k] * W[dy][dx][k][c]        (3 A windows instead of 9, N = 3 x 2 Cout)
 //   out[p][c]   = Y[p-1][-1][c] + Y[p][0][c] + Y[p+1][+1][c]           (epilogue: warp shuffles between TMEM lanes)
 // A tile therefore carries 128 rows of Y but owns 126 outputs (rows 1..126); tiles advance by 126 positions.
-// Weight image per layer: [dy 3][chunk Cin/8][6 Cout rows: hi dx-1 | hi dx0 | hi dx+1 | lo dx-1 | lo dx0 | lo dx+1][8].
+// Weight image per layer: [dy 3][chunk Cin/8][6 Cout rows: hi dx-1 | hi dx0 | hi dx+1 | lo dx-1 | lo dx0 | lo dx+1][8];
+// the three split products (hi*hi, hi*lo, lo*hi) are three N = 3 Cout MMAs into the same accumulator columns.
 constexpr int DX_TILE = 126;
-constexpr int DX_DCOLS = 192;  // accumulator columns per slot (6 x 32)
+constexpr int DX_DCOLS = 96;   // accumulator columns per slot (3 dx x 32)
+constexpr int DX_THREADS = 640;  // producer, issuer, 2 idle warps, 4 epilogue groups of 4 warps
 
 template <int CIN, int NPAD>
 __device__ __forceinline__ void issue_conv_dx(uint32_t st_addr, uint32_t w_addr, uint32_t d) {
   constexpr int KC = CIN / 8;
-  constexpr uint32_t IDESC_ALL = make_idesc(6 * NPAD, 128);  // A_hi x [W_hi (3 dx) | W_lo (3 dx)]
-  constexpr uint32_t IDESC_HI = make_idesc(3 * NPAD, 128);   // A_lo x  W_hi (3 dx)
+  constexpr uint32_t IDESC = make_idesc(3 * NPAD, 128);  // three dx taps side by side
   uint32_t acc = 0;
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
@@ -672,24 +673,20 @@ __device__ __forceinline__ void issue_conv_dx(uint32_t st_addr, uint32_t w_addr,
     for (int ks = 0; ks < CIN / 16; ++ks) {
       const uint32_t a_hi = st_addr + (uint32_t)((2 * ks) * 2) * ENC_WIN_B + (uint32_t)shift * 16;
       const uint32_t a_lo = a_hi + ENC_WIN_B;
+      const uint64_t da_hi = make_desc_interleave(a_hi, 2 * ENC_WIN_B, 128);
+      const uint64_t da_lo = make_desc_interleave(a_lo, 2 * ENC_WIN_B, 128);
+      // rows [0, 3 NPAD) of the (dy, chunk) block = W_hi of the three taps, rows [3 NPAD, 6 NPAD) = W_lo
       const uint32_t b = w_addr + (uint32_t)((dy * KC + 2 * ks) * 6 * NPAD) * 16;
-      const uint64_t db = make_desc_interleave(b, 6 * NPAD * 16, 128);
-      mma_ss(d, make_desc_interleave(a_hi, 2 * ENC_WIN_B, 128), db, IDESC_ALL, acc);
-      mma_ss(d, make_desc_interleave(a_lo, 2 * ENC_WIN_B, 128), db, IDESC_HI, 1);
+      const uint64_t db_hi = make_desc_interleave(b, 6 * NPAD * 16, 128);
+      const uint64_t db_lo = make_desc_interleave(b + 3 * NPAD * 16, 6 * NPAD * 16, 128);
+      // all three split products accumulate into the SAME 3 NPAD columns: the accumulator stays 96 columns wide
+      // (four slots in TMEM, epilogue decoupled from the MMAs) at the price of reading A_hi twice
+      mma_ss(d, da_hi, db_hi, IDESC, acc);
+      mma_ss(d, da_hi, db_lo, IDESC, 1);
+      mma_ss(d, da_lo, db_hi, IDESC, 1);
       acc = 1;
     }
   }
-}
-
-// 8 channels of Y[.][dx] of this thread's row: columns dx*NPAD + c (hi weights) + 3*NPAD + dx*NPAD + c (lo weights)
-template <int NPAD>
-__device__ __forceinline__ void load_y8(uint32_t taddr, int dx, int kc, float (&y)[8]) {
-  uint32_t a[8], b[8];
-  tmem_ld8(taddr + dx * NPAD + kc * 8, a);
-  tmem_ld8(taddr + 3 * NPAD + dx * NPAD + kc * 8, b);
-  tc_wait_ld();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
 }
 
 template <int NPAD>
@@ -697,38 +694,47 @@ __device__ __forceinline__ void epilogue_dx(uint32_t taddr, float* xch, int quad
                                             const uint8_t* res_map, bool relu, bool owner, bool valid, int pos,
                                             uint8_t* out_map, float* out_img, int cout) {
   const int lane = threadIdx.x & 31;
+  if (res_map != nullptr && owner) {  // the residual rows are needed at the very end: start fetching them now
+    const uint8_t* rp = res_map + (size_t)(ENC_GUARD + (pos < 0 ? 0 : pos)) * 16;
+#pragma unroll
+    for (int pl = 0; pl < NPAD / 4; ++pl) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + (size_t)pl * ENC_PLANE_B));
+  }
+  // the dx = -1 and dx = +1 blocks of this row in one go (one wait for all the TMEM loads)
+  uint32_t ym[NPAD], yp[NPAD];
+#pragma unroll
+  for (int c = 0; c < NPAD; c += 16) {
+    tmem_ld16(taddr + c, reinterpret_cast<uint32_t(&)[16]>(ym[c]));
+    tmem_ld16(taddr + 2 * NPAD + c, reinterpret_cast<uint32_t(&)[16]>(yp[c]));
+  }
+  tc_wait_ld();
   // rows at the warp boundaries travel through shared memory: xch[warp][0] = Y[-1 block] of lane 31 (for the next warp's
   // lane 0), xch[warp][1] = Y[+1 block] of lane 0 (for the previous warp's lane 31)
+  if (lane == 31) {
 #pragma unroll
-  for (int kc = 0; kc < NPAD / 8; ++kc) {
-    float y[8];
-    load_y8<NPAD>(taddr, 0, kc, y);
-    if (lane == 31) {
+    for (int c = 0; c < NPAD; ++c) xch[quad * 64 + c] = __uint_as_float(ym[c]);
+  }
+  if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xch[quad * 64 + kc * 8 + j] = y[j];
-    }
-    load_y8<NPAD>(taddr, 2, kc, y);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xch[quad * 64 + 32 + kc * 8 + j] = y[j];
-    }
+    for (int c = 0; c < NPAD; ++c) xch[quad * 64 + 32 + c] = __uint_as_float(yp[c]);
   }
   group_bar(1 + eg, 128);
   const size_t plane_off = (size_t)(ENC_GUARD + (pos < 0 ? 0 : pos)) * 16;
 #pragma unroll
   for (int kc = 0; kc < NPAD / 8; ++kc) {
-    float ym[8], y0[8], yp[8], v[8];
-    load_y8<NPAD>(taddr, 0, kc, ym);
-    load_y8<NPAD>(taddr, 1, kc, y0);
-    load_y8<NPAD>(taddr, 2, kc, yp);
+    uint32_t y0[8];
+    tmem_ld8(taddr + NPAD + kc * 8, y0);
+    float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float left = __shfl_up_sync(0xffffffffu, ym[j], 1);     // Y[p-1][dx = -1]
-      float right = __shfl_down_sync(0xffffffffu, yp[j], 1);  // Y[p+1][dx = +1]
+      float left = __shfl_up_sync(0xffffffffu, __uint_as_float(ym[kc * 8 + j]), 1);     // Y[p-1][dx = -1]
+      float right = __shfl_down_sync(0xffffffffu, __uint_as_float(yp[kc * 8 + j]), 1);  // Y[p+1][dx = +1]
       if (lane == 0 && quad > 0) left = xch[(quad - 1) * 64 + kc * 8 + j];
       if (lane == 31 && quad < 3) right = xch[(quad + 1) * 64 + 32 + kc * 8 + j];
-      v[j] = (left + y0[j]) + right + bias_s[kc * 8 + j];
+      v[j] = left + right + bias_s[kc * 8 + j];
     }
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += __uint_as_float(y0[j]);
     if (res_map != nullptr && owner) {
       const uint8_t* rp = res_map + (size_t)(kc * 2) * ENC_PLANE_B + plane_off;
       float x[8];
@@ -757,7 +763,9 @@ __device__ __forceinline__ void epilogue_dx(uint32_t taddr, float* xch, int quad
   }
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_dx(const __grid_constant__ TrunkParams P) {
+// four epilogue groups (warps 4-19), one per accumulator slot: the epilogue (global stores + release per tile) is
+// latency-bound, the MMA side no longer is
+__global__ void __launch_bounds__(DX_THREADS, 1) k_enc_trunk_dx(const __grid_constant__ TrunkParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
   uint8_t* stage0 = smem + ((TR_W_B + 127) & ~127);
@@ -856,8 +864,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_dx(const __grid_co
           for (int tile = 0; tile < ENC_TILES; ++tile, ++c) {
             const int s = (int)(c % ENC_STAGES);
             const uint32_t par = (uint32_t)((c / ENC_STAGES) & 1);
-            const int slot = (int)(c & 1);                       // accumulator slot == epilogue group
-            const uint32_t dpar = (uint32_t)((c >> 1) & 1);
+            const int slot = s;                                  // accumulator slot == shared-memory stage
+            const uint32_t dpar = par;
             mbar_wait(tmem_free + slot, dpar ^ 1u);
             mbar_wait(full + s, par);
             tc_fence_after();
@@ -926,7 +934,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_dx(const __grid_co
     // image k (one stem tile every fourth item), where the epilogue warps would otherwise wait for the tensor pipe
     if ((long long)blockIdx.x < P.n_images)
       for (int tile = 0; tile < ENC_TILES; ++tile)
-        if ((tile & 1) == eg) stem_tile(blockIdx.x, 0, tile);
+        if ((tile & 3) == eg) stem_tile(blockIdx.x, 0, tile);
     long long c = 0;
     int k = 0;
     for (long long image = blockIdx.x; image < P.n_images; image += gridDim.x, ++k) {
@@ -935,16 +943,17 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_dx(const __grid_co
       int j = 0;
       for (int layer = 1; layer <= 4; ++layer) {
         for (int tile = 0; tile < ENC_TILES; ++tile, ++c, ++j) {
-          if ((j & 3) == 0 && (j >> 2) < ENC_TILES && next < P.n_images && (((j >> 2) & 1) == eg)) stem_tile(next, k + 1, j >> 2);
-          if ((int)(c & 1) != eg) continue;
+          if ((j & 3) == 0 && (j >> 2) < ENC_TILES && next < P.n_images && (((j >> 2) & 3) == eg)) stem_tile(next, k + 1, j >> 2);
+          if ((int)(c & 3) != eg) continue;
           const int pos = tile * DX_TILE - 1 + r;              // this thread's ROW of Y; it owns output `pos` if 1 <= r <= 126
           const bool owner = r >= 1 && r <= DX_TILE;
           const bool valid = owner && pos >= 0 && enc_valid(pos);
-          const uint32_t dpar = (uint32_t)((c >> 1) & 1);
-          mbar_wait(mma_done + eg, dpar);
+          const int slot = (int)(c % ENC_STAGES);
+          const uint32_t dpar = (uint32_t)((c / ENC_STAGES) & 1);
+          mbar_wait(mma_done + slot, dpar);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + eg * DX_DCOLS + ((uint32_t)(quad * 32) << 16);
-          float* my_xch = xch + ((size_t)(eg * 2 + (int)((c >> 1) & 1)) * 4) * 64;
+          const uint32_t taddr = tmem_base + slot * DX_DCOLS + ((uint32_t)(quad * 32) << 16);
+          float* my_xch = xch + ((size_t)(eg * 2 + (int)((c >> 2) & 1)) * 4) * 64;
           const float* bias_s = reinterpret_cast<const float*>(
               w_s + OFF_W[layer] + (layer <= 2 ? TR_W2_B - 128 : layer == 3 ? TR_W3_B - 64 : TR_W4_B - 64));
           float* out_img = P.out_nchw + (size_t)image * P.cout * 1024;
@@ -954,7 +963,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) k_enc_trunk_dx(const __grid_co
           else epilogue_dx<16>(taddr, my_xch, quad, eg, bias_s, nullptr, false, owner, valid, pos, nullptr, out_img, P.cout);
           tc_fence_before();
           __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(tmem_free + eg);
+          if ((tid & 31) == 0) mbar_arrive(tmem_free + slot);
           if (layer < 4) publish_tile(tile_done + (layer - 1) * ENC_TILES + tile);
         }
       }
@@ -994,7 +1003,7 @@ int launch_enc_trunk(int n_images, int cout, const float* images, const void* we
   P.out_nchw = out_nchw;
   P.n_images = n_images;
   P.cout = cout;
-  const size_t smem = ((TR_W_B + 127) & ~127) + (size_t)ENC_STAGES * TR_STAGE_B + 1024 + 4096;
+  const size_t smem = ((TR_W_B + 127) & ~127) + (size_t)ENC_STAGES * TR_STAGE_B + 1024 + 8192;
   static thread_local int configured_dev = -1;
   static thread_local size_t window = 0;
   int dev = 0, grid = 148;
@@ -1014,13 +1023,13 @@ int launch_enc_trunk(int n_images, int cout, const float* images, const void* we
   // MMF_ENC_VARIANT (parity-green, measured per 16,384 images on B200):
   //   0 = one MMA pair per tap and K step, A windows read from shared memory by the MMAs (default, 5.2 ms)
   //   3 = the three dx taps of a stencil row stacked along N, the dx shift applied in the epilogue with warp shuffles:
-  //       a third of the A reads and MMAs (tensor pipe no longer the limiter), but the heavier epilogue with only two
-  //       192-column accumulator slots currently makes it 6.4 ms
+  //       a third of the A windows and MMAs (with the epilogue body disabled the pipeline runs in 3.7 ms), four epilogue
+  //       groups; as built the epilogue is the limiter and it lands at 4.9 ms, level with variant 0 on the same box
   // (TS-form variants -- A through a TMEM ring filled by gather warps, 5.5-5.7 ms -- were measured and removed, see
   //  DESIGN.md section 3.2 and the git history.)
   int variant = 0;
   if (const char* env = getenv("MMF_ENC_VARIANT")) variant = atoi(env);
-  if (variant == 3) k_enc_trunk_dx<<<grid, ENC_THREADS, smem, stream>>>(P);
+  if (variant == 3) k_enc_trunk_dx<<<grid, DX_THREADS, smem, stream>>>(P);
   else k_enc_trunk<<<grid, ENC_THREADS, smem, stream>>>(P);
   MMF_LAUNCH_CHECK("k_enc_trunk");
   return MMF_OK;
