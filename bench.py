@@ -222,7 +222,8 @@ def bptt_arm(args):
         p.requires_grad_(False)
     for p in trainable:
         p.requires_grad_(True)
-    opt = torch.optim.Adam(trainable, lr=1e-4, fused=True)  # one multi-tensor kernel instead of ~10 launches per tensor
+    # fused: one multi-tensor kernel instead of ~10 launches per tensor; capturable: the step may live in a CUDA graph
+    opt = torch.optim.Adam(trainable, lr=1e-4, fused=True, capturable=True)
     g = torch.Generator(device=dev).manual_seed(rank)
     feats = [torch.randn(T, N, 64, device=dev, generator=g), torch.randn(T, N, 128, device=dev, generator=g)]
     wm_feats = torch.randn(T, N, 192, device=dev, generator=g)
@@ -250,31 +251,82 @@ def bptt_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    ops.PROFILE.reset(enabled=True)
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        start.record()
-        for _ in range(args.steps):
-            loss = step()
-        stop.record()
+    graph, static_loss, eager_ms = None, None, None
+    use_graph = world == 1 and not os.environ.get("MMF_BENCH_NO_GRAPH")
+    if not use_graph:
+        # multi-GPU (or MMF_BENCH_NO_GRAPH): eager steps on the default stream, NCCL all-reduce between backward and Adam.
+        # (capturing the NCCL all-reduce inside the step graph hung at 2 GPUs in round 1: not used.)
+        for _ in range(args.warmup):
+            step()
         barrier()
-    prof = ops.PROFILE.collect()
-    ops.PROFILE.reset(enabled=False)
+        ops.PROFILE.reset(enabled=True)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            start.record()
+            for _ in range(args.steps):
+                loss = step()
+            stop.record()
+            barrier()
+        prof = ops.PROFILE.collect()
+        ops.PROFILE.reset(enabled=False)
+        for v in prof["kernels"].values():
+            v["total_ms"] /= args.steps
+        prof["launches"] //= args.steps
+    else:
+        # single GPU: warm-up on a side stream (as torch.cuda.graph wants it), one eager step with per-kernel events, then
+        # the whole training step -- forward, backward, Adam -- is captured in ONE CUDA graph and replayed: the eager
+        # step is bound by ~20 ms of Python / autograd dispatch for ~17 ms of kernels
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # every backward runs on `side`: autograd's AccumulateGrad nodes stay there
+            for _ in range(args.warmup):
+                step()
+            side.synchronize()
+            ops.PROFILE.reset(enabled=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = step()
+            e1.record()
+            prof = ops.PROFILE.collect()
+            ops.PROFILE.reset(enabled=False)
+            eager_ms = e0.elapsed_time(e1)
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    static_loss = step()
+                graph.replay()  # first replay outside the timed region
+                side.synchronize()
+            except Exception as exc:
+                # a failed capture leaves the generator / stream state unusable: start over without the graph
+                print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); restarting with eager steps",
+                      file=sys.stderr, flush=True)
+                os.environ["MMF_BENCH_NO_GRAPH"] = "1"
+                os.execv(sys.executable, [sys.executable] + sys.argv)
+        torch.cuda.current_stream().wait_stream(side)
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk, torch.cuda.stream(side):
+            start.record()
+            for _ in range(args.steps):
+                graph.replay()
+            loss = static_loss
+            stop.record()
+            side.synchronize()
+            barrier()
     ms = max_over_ranks(start.elapsed_time(stop), dev) / args.steps
     units = N * Mp * T
     if rank == 0:
-        kern = {k: {"avg_ms": v["avg_ms"], "share": v["total_ms"] / (ms * args.steps)} for k, v in prof["kernels"].items()}
+        kern = {k: {"avg_ms": v["avg_ms"], "share": v["total_ms"] / ms} for k, v in prof["kernels"].items()}
         line = {
             "metric": "particle-steps/sec", "value": world * units / (ms / 1e3), "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": filt.precision, "data": "synthetic",
             "config": {"workload": cfg, "id": "c4", "model": name, "trajectories_per_gpu": N, "particles": Mp,
                        "filter_steps_per_pass": T, "phases": "forward + backward + grad all-reduce + Adam",
-                       "encoders": "hoisted and frozen (features are inputs)", "final_loss": float(loss.detach())},
-            "clocks": clk.summary(), "gpu_launches": prof["launches"], "kernels": kern,
+                       "encoders": "hoisted and frozen (features are inputs)", "final_loss": float(loss.detach()),
+                       "launch": "one CUDA graph per training step" if graph is not None else "eager",
+                       "eager_ms_per_step": eager_ms},
+            "clocks": clk.summary(), "gpu_launches": prof["launches"] * args.steps, "kernels": kern,
             "e2e": {"value": world * units / (ms / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 4, "note": "training step is device-resident; loss scalar read back"},
         }

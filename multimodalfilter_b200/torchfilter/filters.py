@@ -177,10 +177,15 @@ class ParticleFilter(Filter):
         eps = self._process_eps(N * M, sd, states)
         moved, ll = training.FusedHeads.apply(plan, states, eps, dyn_row, torch.stack(rows), plan.enabled_mask(),
                                              ops.PRECISIONS[self.precision], *params)
-        ll = ll[[k for k, on in enumerate(enabled) if on]].permute(1, 2, 0)  # (N, M, K_enabled)
+        # select the enabled heads by slicing: indexing with a Python list would build the index tensor on the host and
+        # copy it over (a synchronising H2D copy per step, and not capturable in a CUDA graph)
+        on_idx = [k for k, on in enumerate(enabled) if on]
+        all_on = len(on_idx) == len(enabled)
+        ll = (ll if all_on else torch.stack([ll[k] for k in on_idx])).permute(1, 2, 0)  # (N, M, K_enabled)
         modw = plan.modality_log_weights(observations) if hoisted is None else hoisted[1]
         if modw is not None:
-            ll = ll + modw[:, enabled][:, None, :]
+            mw = modw if all_on else torch.stack([modw[:, k] for k in on_idx], dim=1)
+            ll = ll + mw[:, None, :]
         logw_unnorm = logw + torch.logsumexp(ll, dim=2)
         logw_n = logw_unnorm - torch.logsumexp(logw_unnorm, dim=1, keepdim=True)
         if self.estimation_method == "weighted_average":
