@@ -187,3 +187,75 @@ def test_install_aliases_make_reference_imports_resolve():
     ) % REPO
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "OK" in res.stdout, res.stderr[-3000:]
+
+
+# ---- image-encoder operand images (layouts documented in include/mmf_b200.h) -----------------------------
+def _bf16_pairs(buf, count):
+    """uint8 tensor -> float32 values of `count` bf16 numbers"""
+    return buf[: 2 * count].view(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (32, 16), (16, 8)])
+def test_conv3x3_operand_image_layout(cin, cout):
+    """mmf_enc_conv3x3's w_image: bf16 [tap 9][cin/8][2 npad rows: hi then lo][8] + fp32 bias[npad]; hi + lo restores
+    the fp32 weight to 2^-17 and padded rows are zero."""
+    from multimodalfilter_b200 import ops
+
+    torch.manual_seed(cin + cout)
+    conv = torch.nn.Conv2d(cin, cout, 3, padding=1)
+    npad = 32 if cout > 16 else 16
+    img = ops.enc_pack_conv3x3(conv)
+    n_w = 9 * (cin // 8) * 2 * npad * 8
+    assert img.numel() == 2 * n_w + 4 * npad
+    w = _bf16_pairs(img, n_w).reshape(9, cin // 8, 2, npad, 8)          # (tap, chunk, hi|lo, row, channel-in-chunk)
+    rebuilt = (w[:, :, 0] + w[:, :, 1]).permute(2, 1, 3, 0).reshape(npad, cin, 3, 3)  # (row, cin, ky, kx)
+    ref = conv.weight.detach()
+    assert torch.allclose(rebuilt[:cout], ref, rtol=0, atol=float(ref.abs().max()) * 2 ** -16)
+    assert rebuilt[cout:].abs().max() == 0 if cout < npad else True
+    bias = img[2 * n_w:].view(torch.float32)
+    assert torch.equal(bias[:cout], conv.bias.detach()) and (bias[cout:] == 0).all()
+
+
+def test_conv3x3_dx_stacked_image_layout():
+    """MMF_ENC_VARIANT=3: bf16 [dy 3][cin/8][6 npad rows: hi dx-1 | hi dx0 | hi dx+1 | lo dx-1 | lo dx0 | lo dx+1][8]."""
+    from multimodalfilter_b200 import ops
+
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(32, 16, 3, padding=1)
+    cin, cout, npad = 32, 16, 16
+    img = ops.enc_pack_conv3x3_dx(conv)
+    n_w = 3 * (cin // 8) * 6 * npad * 8
+    w = _bf16_pairs(img, n_w).reshape(3, cin // 8, 2, 3, npad, 8)       # (ky, chunk, hi|lo, kx, row, channel-in-chunk)
+    rebuilt = (w[:, :, 0] + w[:, :, 1]).permute(3, 1, 4, 0, 2).reshape(npad, cin, 3, 3)
+    ref = conv.weight.detach()
+    assert torch.allclose(rebuilt[:cout], ref, rtol=0, atol=float(ref.abs().max()) * 2 ** -16)
+
+
+def test_stem_and_trunk_weight_buffers():
+    from multimodalfilter_b200 import ops
+    from multimodalfilter_b200.crossmodal import models as M
+    from multimodalfilter_b200.encoders import ImageEncoder
+
+    enc = M.PushCrossmodalParticleFilter().measurement_model.measurement_models[0].observation_image_layers
+    assert isinstance(enc, ImageEncoder)
+    convs = enc._trunk()
+    assert convs is not None and [c.out_channels for c in convs] == [32, 32, 32, 16, 8]
+    stem = ops.enc_pack_stem(convs[0])
+    assert stem.shape == (25 * 32 + 32,)
+    assert torch.equal(stem[: 25 * 32].reshape(25, 32).t().reshape(32, 1, 5, 5), convs[0].weight.detach())
+    # the spanning-average-pool variant of the encoder is not the fused architecture: plain torch path
+    pooled = M._image_encoder(64, spanning_avg_pool=True)
+    assert pooled._trunk() is None
+    # on CPU tensors / with autograd the module is the reference nn.Sequential
+    y = enc(torch.zeros(2, 1, 32, 32))
+    assert y.shape == (2, 64) and y.requires_grad
+
+
+def test_chunk_major_rows_view_round_trip():
+    """act / delta planes of the BPTT kernels: [column / 4][row][4] <-> (rows, 64)."""
+    from multimodalfilter_b200 import ops
+
+    rows = torch.arange(5 * 64, dtype=torch.float32).reshape(5, 64)
+    planes = rows.reshape(5, 16, 4).transpose(0, 1).contiguous()        # (16, 5, 4)
+    assert torch.equal(ops.rows_view(planes), rows)
+    assert torch.equal(ops.rows_view(planes[None, None]), rows[None, None])
