@@ -143,18 +143,53 @@ def check(rc: int) -> None:
         raise MMFError(f"libmmf_b200 error {rc}: {msg.decode() if msg else '?'}")
 
 
+_tls = threading.local()
+
+
 def ptr(t):
-    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    """Device pointer of a contiguous CUDA tensor (None -> NULL).  The tensor's device is noted so that ``call`` can
+    check that every buffer of one launch lives on the device the kernels are launched on."""
     if t is None:
         return None
     if not t.is_cuda:
         raise MMFError("libmmf_b200 only takes CUDA tensors: there is no CPU path")
     if not t.is_contiguous():
         raise MMFError("libmmf_b200 needs C-contiguous tensors")
+    seen = getattr(_tls, "devices", None)
+    if seen is None:
+        seen = _tls.devices = []
+    seen.append(t.device)
     return C.c_void_p(t.data_ptr())
+
+
+class Stream(C.c_void_p):
+    """``cudaStream_t`` argument that remembers which device it belongs to."""
+
+    device = None
 
 
 def stream_of(t):
     import torch
 
-    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    s = Stream(torch.cuda.current_stream(t.device).cuda_stream)
+    s.device = t.device
+    return s
+
+
+def call(fn, *args):
+    """Run one C entry point with the CUDA device of its stream argument current.  The launchers configure and launch
+    on the process-current device (cudaGetDevice), so a filter living on cuda:1 while cuda:0 is current must switch
+    devices around the call; buffers on any other device than the stream's are refused."""
+    import torch
+
+    seen, _tls.devices = getattr(_tls, "devices", None) or [], []
+    stream = next((a for a in reversed(args) if isinstance(a, Stream)), None)
+    if stream is None or stream.device is None:
+        return fn(*args)
+    for d in seen:
+        if d != stream.device:
+            raise MMFError(f"all buffers of one libmmf_b200 call must live on one device: got {d} and {stream.device}")
+    if torch.cuda.current_device() == stream.device.index:
+        return fn(*args)
+    with torch.cuda.device(stream.device):
+        return fn(*args)

@@ -444,9 +444,9 @@ class _MultiFilter(tf_base.Filter, _EnabledModels):
         return [f for f, on in zip(self.filter_models, self._enabled_models) if on]
 
     def _plan(self, filters):
-        key = tuple(id(f.dynamics_model) for f in filters)
+        key = tuple(f.dynamics_model for f in filters)  # the modules themselves, compared by identity
         cached = self.__dict__.get("_mmf_plan")
-        if cached is None or cached[0] != key:
+        if cached is None or len(cached[0]) != len(key) or any(a is not b for a, b in zip(cached[0], key)):
             ok = all(isinstance(f, tf_filters.VirtualSensorExtendedKalmanFilter) for f in filters)
             cached = (key, fused.EKFPlan.build(filters) if ok else None)
             self.__dict__["_mmf_plan"] = cached

@@ -26,11 +26,6 @@
 
 namespace mmf {
 
-// Debug-only phase timestamps of (CTA 0, group 0, thread 0): enabled with MMF_TC_TIMESTAMPS=1, read back with
-// mmf_debug_tc_timestamps().  Layout: per layer iteration 5 clock64 stamps.
-__device__ unsigned long long g_tc_stamps[8192];
-__device__ unsigned int g_tc_stamp_count;
-
 struct TcParams {
   ChainDev chains[1 + MMF_MAX_HEADS];
   const uint8_t* images[1 + MMF_MAX_HEADS];
@@ -38,7 +33,6 @@ struct TcParams {
   uint32_t enabled;
   int sd, N, M, single_pass;
   uint32_t wait_hint_ns;
-  int stamps, use_lock;
   int first_chain;   // 0: dynamics + heads; 1: heads only (states_out already holds the moved particles)
   float* act_out;    // training: (K, L+1, N*M, 64) fp32 activations feeding every GEMM layer of every head, or null
   long long total;
@@ -208,11 +202,6 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
   uint64_t* gbar = wbar + 1;                      // MMA-done, one per group (both CTAs in PAIR mode)
   uint64_t* ready = gbar + TC_MAX_GROUPS;         // PAIR: A operand ready in both CTAs (lives in the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + TC_MAX_GROUPS);
-  // Turnstile for the tensor pipe: a group issues its whole batch of MMAs (one layer) while holding it.
-  // Without it the four issuing threads interleave their MMAs one by one, all groups finish their layers at
-  // the same moment and the kernel degenerates into "everybody in the epilogue, then everybody queueing at
-  // the tensor pipe" (measured with the phase timestamps below); batches served one at a time stagger the groups.
-  uint32_t* mma_lock = tmem_slot + 1;
 
   const int tid = threadIdx.x, gt = tid & 127;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
@@ -223,7 +212,6 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
   const uint32_t rank = PAIR ? cluster_ctarank() : 0;
 
   if (tid == 0) {
-    *mma_lock = 0;
     mbar_init(wbar, 1);
     for (int i = 0; i < TC_GROUPS; ++i) {
       mbar_init(gbar + i, 1);
@@ -355,15 +343,10 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
       // ---- 64x64 layers ----------------------------------------------------------------------------------
       for (int layer = 0; layer <= L; ++layer) {
         const bool is_out = (layer == L);
-        const bool stamp = P.stamps && blockIdx.x == 0 && tid == 0 && c == 0 && it == 1;
-        unsigned long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0;
-        if (stamp) ts0 = clock64();
         // hand the A operand to the tensor core
         tc_wait_st();
         tc_fence_before();
-        if (stamp) ts1 = clock64();
         group_bar(1 + g, 128);
-        if (stamp) ts2 = clock64();
         if ((warp & 3) == 0 && elect_one_sync()) {  // one lane of the group's first warp issues
           bool issue = true;
           if (PAIR) {
@@ -372,9 +355,6 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
             if (issue) mbar_wait_cluster(ready + g, rphase);
           }
           if (issue) {
-            if (P.use_lock) {
-              while (atomicCAS(mma_lock, 0u, 1u) != 0u) __nanosleep(20);
-            }
             tc_fence_after();
             const uint32_t hi_addr = tiles_addr + (is_out ? (uint32_t)L * 2 * TILE : (uint32_t)layer * 2 * TILE);
             const uint32_t lo_addr = hi_addr + (is_out ? OUT_TILE_B : TILE);
@@ -402,24 +382,12 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
               }
               tc_commit(gbar + g);
             }
-            if (P.use_lock) atomicExch(mma_lock, 0u);
           }
         }
         rphase ^= 1;
-        if (stamp) ts3 = clock64();
         mbar_wait(gbar + g, gphase, P.wait_hint_ns);
         gphase ^= 1;
         tc_fence_after();
-        if (stamp) {
-          const unsigned int slot = atomicAdd(&g_tc_stamp_count, 1u);
-          if (slot < 1600) {
-            g_tc_stamps[slot * 5 + 0] = ts0;
-            g_tc_stamps[slot * 5 + 1] = ts1;
-            g_tc_stamps[slot * 5 + 2] = ts2;
-            g_tc_stamps[slot * 5 + 3] = ts3;
-            g_tc_stamps[slot * 5 + 4] = clock64();
-          }
-        }
         if (is_out) break;
 
         // ---- epilogue of this layer = producer of the next layer's A operand ---------------------------
@@ -492,105 +460,84 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
 }
 
 
-// ---- pipelined variant (MMF_TC_VARIANT=51) ------------------------------------------------------------------
-// Same tiles, same arithmetic per layer, different hand-over between the CUDA cores and the tensor pipe:
-//   * every group has a dedicated issuer warp (warp 4*G + g) that issues its tcgen05.mma; the 128 threads of a
-//     group never meet at a barrier, they only arrive on mbarriers;
-//   * the next A operand is written IN PLACE over the accumulator chunk it was computed from (16 fp32 columns ->
-//     8 columns of bf16x2 hi + 8 columns of lo) and the accumulator ping-pongs between the two 64-column halves
-//     of the group's TMEM slice, so K step k of layer l+1 is issued as soon as chunk k of layer l's epilogue is
-//     done, while the group is still working on chunks k+1...: the group's serial chain per layer shrinks from
-//     "epilogue + 12 MMAs + commit latency" to "epilogue + 3 MMAs + commit latency".
-// publish chunk `chunk` of the A operand: stores retired -> ordered before the arrive the issuer observes
-__device__ __forceinline__ void publish_chunk(uint64_t* cbar, int chunk) {
-  tc_wait_st();
-  tc_fence_before();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(cbar + chunk);  // one arrival per warp: 128 lanes on one mbarrier serialise
-}
-
-// tbuf / bias4 / act_row / cbar already point at this thread's first column (chunk); NCH chunks of 16 columns
-template <int KIND, int NCH>
-__device__ __forceinline__ void epilogue_pipe(uint32_t tbuf, const float4* __restrict__ bias4, float2 (&xr)[NCH * 8],
-                                              bool single_pass, float* act_row, size_t act_stride4, uint64_t* cbar) {
-  uint32_t d[2][16];
-  tmem_ld16(tbuf, d[0]);
-  tc_wait_ld();
+// ---- warp-specialised kernel (the default, MMF_TC_VARIANT=71): ONE issuer warp feeds the tensor pipe -------------
+// In the symmetric kernel above every group issues its own MMAs.  The four issuing lanes block on the tensor
+// pipe's queue and their instructions interleave one by one in its FIFO, so the four accumulators complete at the
+// same moment and the SM alternates between "all groups in the epilogue" (issue-slot bound) and "all groups queued
+// at the tensor pipe": a layer costs epilogue time PLUS MMA time (ncu r01: tensor pipe 52 %, issue slots 59 %, and
+// 870 cycles per tile-layer = 450 issue + 384 tensor) instead of their maximum.  Here warp 4 G issues everything
+// and serves the groups round robin, one group's MMAs back to back: accumulators complete 384 cycles apart, the
+// groups' epilogues stay staggered, and the epilogue warps lose the issue code, the per-layer named barrier and
+// the divergent single-lane region from their instruction stream.
+//   a_ready[g] (count 4): a warp of group g arrives once its part of the next A operand is in TMEM
+//   d_ready[g][h] (count 1): tcgen05.commit after the MMAs of (half h of) group g's accumulator
+// SPLIT = 2 issues a layer as two N = 32 batches, columns [0, 32) first: the group starts its epilogue on the
+// first half while the tensor pipe is still on the second.
+template <int KIND, int SPLIT>
+__device__ __forceinline__ void epilogue_ws(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float4* __restrict__ bias4,
+                                            float2 (&xr)[U / 2], bool single_pass, float* act_row, size_t act_stride4,
+                                            uint64_t* dbar, uint32_t (&dph)[2]) {
+  if (SPLIT == 1) {
+    mbar_wait(dbar, dph[0]);
+    dph[0] ^= 1;
+    tc_fence_after();
+    epilogue<KIND, U>(tD, tAhi, tAlo, bias4, xr, single_pass, act_row, act_stride4);
+  } else {
 #pragma unroll
-  for (int chunk = 0; chunk < NCH; ++chunk) {
-    if (chunk + 1 < NCH) tmem_ld16(tbuf + (chunk + 1) * 16, d[(chunk + 1) & 1]);
-    float2 b[8];
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      const float4 t = (KIND >= EPI_MID_RELU) ? __ldg(bias4 + chunk * 4 + q4) : bias4[chunk * 4 + q4];
-      b[2 * q4] = make_float2(t.x, t.y);
-      b[2 * q4 + 1] = make_float2(t.z, t.w);
+    for (int h = 0; h < 2; ++h) {
+      mbar_wait(dbar + h, dph[h]);
+      dph[h] ^= 1;
+      tc_fence_after();
+      float2(&xh)[U / 4] = *reinterpret_cast<float2(*)[U / 4]>(&xr[h * (U / 4)]);
+      epilogue<KIND, U / 2>(tD + h * (U / 2), tAhi + h * (U / 4), tAlo + h * (U / 4), bias4 + h * (U / 8), xh, single_pass,
+                            act_row ? act_row + (size_t)(h * (U / 8)) * act_stride4 : nullptr, act_stride4);
     }
-    float2 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float2 a = __fadd2_rn(make_float2(__uint_as_float(d[chunk & 1][2 * j]), __uint_as_float(d[chunk & 1][2 * j + 1])), b[j]);
-      if (KIND == EPI_RES_B) a = __fadd2_rn(a, xr[chunk * 8 + j]);
-      if (KIND == EPI_RES_B || KIND == EPI_MID_RELU) {
-        a.x = fmaxf(a.x, 0.0f);
-        a.y = fmaxf(a.y, 0.0f);
-      }
-      if (KIND != EPI_RES_A) xr[chunk * 8 + j] = a;
-      v[j] = a;
-    }
-    if (act_row != nullptr) {
-      if (KIND == EPI_RES_A) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = make_float2(fmaxf(v[j].x, 0.0f), fmaxf(v[j].y, 0.0f));
-      }
-      store_act_chunk(act_row, chunk, v, act_stride4);
-    }
-    // in place: hi -> columns [16 chunk, +8), lo -> [16 chunk + 8, +8) of the buffer just read
-    // chunk-1's stores have had this chunk's arithmetic to retire: publish it now, then store this chunk
-    if (chunk > 0) publish_chunk(cbar, chunk - 1);
-    if (KIND == EPI_RES_A) store_a_chunk<true>(v, tbuf + chunk * 8, tbuf + chunk * 8 + 8, chunk, single_pass);
-    else store_a_chunk<false>(v, tbuf + chunk * 8, tbuf + chunk * 8 + 8, chunk, single_pass);
-    if (chunk + 1 < NCH) tc_wait_ld();
   }
-  publish_chunk(cbar, NCH - 1);
 }
 
-// number of tiles group g of CTA `unit` processes (tile = (it * units + unit) * G + g < tiles)
-__device__ __forceinline__ long long group_tile_count(long long tiles, int G, int g, long long unit, long long units) {
-  const long long slots = tiles > g ? (tiles - g + G - 1) / G : 0;
-  return slots > unit ? (slots - unit + units - 1) / units : 0;
+// start of a chain phase, executed by ALL threads of the CTA: barrier, bulk copy of the chain's operand image into
+// shared memory (one thread), wait.  Every MMA that read the previous image has completed: each group waited for
+// its last accumulator before it got here.
+__device__ __forceinline__ void ws_load_image(const TcParams& P, int c, uint8_t* smem, uint64_t* wbar, uint32_t& wphase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)image_bytes(P.chains[c], 1);
+    const uint8_t* src = P.images[c];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(wbar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768) {
+      const uint32_t n = bytes - off < 32768 ? bytes - off : 32768;
+      bulk_g2s(smem + off, src + off, n, wbar);
+    }
+  }
+  mbar_wait(wbar, wphase);
+  wphase ^= 1;
 }
 
-// TPR = threads per particle row: 1 -> a thread owns all 64 columns of its row; 2 -> two warps share a TMEM lane
-// quadrant and own 32 columns each (twice the warps per scheduler to hide the TMEM / conversion latencies).
-template <int TC_GROUPS, int TPR>
-__global__ void __launch_bounds__(TC_GROUPS * (128 * TPR + 32), 1) k_particle_chain_pipe(const __grid_constant__ TcParams P) {
-  constexpr int CH = U / 16;
-  constexpr int NCH = CH / TPR;       // chunks per thread
-  constexpr int WPG = 4 * TPR;        // worker warps per group
+template <int G, int SPLIT, bool TRAIN>
+__global__ void __launch_bounds__(G * 128 + 128, 1) k_particle_chain_ws(const __grid_constant__ TcParams P) {
+  constexpr int TC_CHUNKS = U / 16;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + P.image_cap);
-  uint64_t* done = wbar + 1;                 // accumulator complete, one per group (tcgen05.commit)
-  uint64_t* cbar = done + TC_MAX_GROUPS;     // A chunk ready, [group][chunk], one arrival per warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cbar + TC_MAX_GROUPS * CH);
+  uint64_t* dbar = wbar + 1;                      // [G][2]
+  uint64_t* abar = dbar + 2 * TC_MAX_GROUPS;      // [G]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(abar + TC_MAX_GROUPS);
 
   const int tid = threadIdx.x;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const bool issuer = warp >= TC_GROUPS * WPG;  // warp G*WPG + i issues the MMAs of group i
-  const int g = issuer ? warp - TC_GROUPS * WPG : warp / WPG;
-  const int wig = warp - g * WPG;               // worker: warp inside the group
-  const int quad = wig & 3;                     // TMEM lane quadrant
-  const int half = wig >> 2;                    // which NCH chunks of the row this thread owns
-  const int row = quad * 32 + (tid & 31);
-  const int col0 = half * NCH * 16;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
+  const bool service = warp >= 4 * G;  // warps 4 G .. 4 G + 3: the issuer and three parked warps (a full warpgroup)
+  const bool issuer = warp == 4 * G;
+  const int g = warp >> 2;
+  const int row = tid & 127;  // particle row inside the tile == TMEM lane (workers)
   const int sd = P.sd;
   const bool single_pass = P.single_pass != 0;
 
   if (tid == 0) {
     mbar_init(wbar, 1);
-    for (int i = 0; i < TC_GROUPS; ++i) {
-      mbar_init(done + i, 1);
-      for (int k = 0; k < CH; ++k) mbar_init(cbar + i * CH + k, 4);
+    for (int i = 0; i < G; ++i) {
+      mbar_init(dbar + 2 * i, 1);
+      mbar_init(dbar + 2 * i + 1, 1);
+      mbar_init(abar + i, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -603,207 +550,232 @@ __global__ void __launch_bounds__(TC_GROUPS * (128 * TPR + 32), 1) k_particle_ch
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-  const uint32_t tG = tmem_base + g * 128 + lane_off;  // this thread's view of its group's slice
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;   // this warp's 32-lane quadrant
+  const uint32_t tD = tmem_base + (service ? 0 : g * 128) + lane_off;
+  const uint32_t tAhi = tD + 64, tAlo = tD + 96;
   uint32_t wphase = 0;
-  // batches[g] = MMA batches (layers) group g has been through so far; its parity is at once the phase of the
-  // group's mbarriers and the half of the slice that holds the A operand.  Workers track their own group.
-  long long batches = 0;
-  uint32_t cur = 0, dphase = 0;
+  uint32_t dph[2] = {0, 0};   // workers: parity of d_ready[g][h]
+  uint32_t aph = 0;           // issuer: bit i = parity of a_ready[i]
 
   const long long tiles = (P.total + 127) / 128;
-  constexpr uint32_t IDESC_L = make_idesc(64, 128);
+  constexpr uint32_t IDESC_L = make_idesc(U / SPLIT, 128);
   constexpr uint32_t IDESC_O = make_idesc(OUT_PAD, 128);
   const long long unit = blockIdx.x, units = gridDim.x;
 
-  for (int c = P.first_chain; c <= P.K; ++c) {
-    if (c > 0 && !((P.enabled >> (c - 1)) & 1u)) continue;
-    const ChainDev ch = P.chains[c];
-    const int L = chain_layers(ch);
-    bool last_head = false, first_head = false;
-    if (c > 0) {
-      last_head = (P.enabled >> c) == 0;
-      first_head = (P.enabled & ((1u << (c - 1)) - 1u)) == 0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)image_bytes(ch, 1);
-      const uint8_t* src = P.images[c];
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(wbar, bytes);
-      for (uint32_t off = 0; off < bytes; off += 32768) {
-        const uint32_t n = bytes - off < 32768 ? bytes - off : 32768;
-        bulk_g2s(smem + off, src + off, n, wbar);
-      }
-    }
-    mbar_wait(wbar, wphase);
-    wphase ^= 1;
-    const uint32_t tiles_addr = smem_u32(smem);
-
-    if (issuer) {
-      // ------------------------------------------------------------------------------- issuer warp of group g
-      const long long my_tiles = group_tile_count(tiles, TC_GROUPS, g, unit, units);
-      if (elect_one_sync()) {
-        const uint32_t slice = tmem_base + g * 128;
-        uint64_t* my_cbar = cbar + g * CH;
-        uint32_t par = (uint32_t)(batches & 1);
-        for (long long t = 0; t < my_tiles; ++t) {
+  if (service) {
+    // Register budget: the CTA is launched with 96 registers per thread (640 threads).  The service warpgroup hands
+    // 64 x 128 registers back to the CTA pool and the four worker warpgroups take 16 x 128 each: 112 registers for
+    // the epilogue (fp32 residual stream 64 + two accumulator chunks in flight 32 + the split).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    for (int c = P.first_chain; c <= P.K; ++c) {
+      if (c > 0 && !((P.enabled >> (c - 1)) & 1u)) continue;
+      const ChainDev ch = P.chains[c];
+      const int L = chain_layers(ch);
+      ws_load_image(P, c, smem, wbar, wphase);
+      if (!issuer) continue;
+      const uint32_t tiles_addr = smem_u32(smem);
+      // ------------------------------------------------------------------------------------------ issuer warp
+        for (long long it = 0;; ++it) {
+          const long long tile0 = (it * units + unit) * G;
+          if (tile0 >= tiles) break;
+          const long long left = tiles - tile0;
+          const int ng = left < G ? (int)left : G;  // groups that have a tile in this slot
           for (int layer = 0; layer <= L; ++layer) {
             const bool is_out = layer == L;
             const uint32_t hi_addr = tiles_addr + (is_out ? (uint32_t)L * 2 * TILE_B : (uint32_t)layer * 2 * TILE_B);
             const uint32_t lo_addr = hi_addr + (is_out ? OUT_TILE_B : TILE_B);
             const uint64_t bhi = make_b_desc(hi_addr), blo = make_b_desc(lo_addr);
-            const uint32_t idesc = is_out ? IDESC_O : IDESC_L;
-            const uint32_t abuf = slice + par * 64, dbuf = slice + (par ^ 1u) * 64;
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-              mbar_wait(my_cbar + k, par);
+            for (int i = 0; i < G; ++i) {
+              if (i >= ng) break;
+              mbar_wait(abar + i, (aph >> i) & 1u);
+              aph ^= 1u << i;
               tc_fence_after();
-              mma_ts(dbuf, abuf + k * 16, bhi + (uint64_t)(k * 2), idesc, k > 0);
-              if (!single_pass) {
-                mma_ts(dbuf, abuf + k * 16, blo + (uint64_t)(k * 2), idesc, 1);
-                mma_ts(dbuf, abuf + k * 16 + 8, bhi + (uint64_t)(k * 2), idesc, 1);
+              if (elect_one_sync()) {
+                const uint32_t d = tmem_base + i * 128, a_hi = d + 64, a_lo = d + 96;
+                if (is_out) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + k * 8, bhi + (uint64_t)(k * 2), IDESC_O, k > 0);
+                  if (!single_pass) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + k * 8, blo + (uint64_t)(k * 2), IDESC_O, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mma_ts(d, a_lo + k * 8, bhi + (uint64_t)(k * 2), IDESC_O, 1);
+                  }
+                  tc_commit(dbar + 2 * i);
+                } else {
+#pragma unroll
+                  for (int h = 0; h < SPLIT; ++h) {
+                    // half h: accumulator columns [32 h, 32 h + 32) = weight rows [32 h, +32) = 4096 h bytes into the tile
+                    const uint64_t bh = bhi + (uint64_t)(h * (4096 >> 4)), bl = blo + (uint64_t)(h * (4096 >> 4));
+                    const uint32_t dh = d + h * (U / 2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mma_ts(dh, a_hi + k * 8, bh + (uint64_t)(k * 2), IDESC_L, k > 0);
+                    if (!single_pass) {
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) mma_ts(dh, a_hi + k * 8, bl + (uint64_t)(k * 2), IDESC_L, 1);
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) mma_ts(dh, a_lo + k * 8, bh + (uint64_t)(k * 2), IDESC_L, 1);
+                    }
+                    tc_commit(dbar + 2 * i + h);
+                  }
+                }
               }
+              __syncwarp();
             }
-            tc_commit(done + g);
-            par ^= 1u;
           }
         }
-      }
-      __syncwarp();
-      batches += my_tiles * (L + 1);
-      continue;
     }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    for (int c = P.first_chain; c <= P.K; ++c) {
+      if (c > 0 && !((P.enabled >> (c - 1)) & 1u)) continue;
+      const ChainDev ch = P.chains[c];
+      const int L = chain_layers(ch);
+      bool last_head = false, first_head = false;
+      if (c > 0) {
+        last_head = (P.enabled >> c) == 0;
+        first_head = (P.enabled & ((1u << (c - 1)) - 1u)) == 0;
+      }
+      ws_load_image(P, c, smem, wbar, wphase);
 
-    // ---------------------------------------------------------------------------------------------- worker groups
-    const float* fsm = reinterpret_cast<const float*>(smem + image_tiles_bytes(ch, 1));
-    const float* in_Wt = fsm;
-    const float* in_b = fsm + ch.in_dim * U;
-    const float* biases = in_b + U;
-    const float* out_b = biases + L * U;
-    const int mid_at = 2 * ch.n_pre;
-    uint64_t* my_cbar = cbar + g * CH + half * NCH;
+      // --------------------------------------------------------------------------------------------- worker groups
+      const float* fsm = reinterpret_cast<const float*>(smem + image_tiles_bytes(ch, 1));
+      const float* in_Wt = fsm;
+      const float* in_b = fsm + ch.in_dim * U;
+      const float* biases = in_b + U;
+      const float* out_b = biases + L * U;
+      const int mid_at = 2 * ch.n_pre;
+      uint64_t* my_dbar = dbar + 2 * g;
 
-    for (long long it = 0;; ++it) {
-      const long long tile = (it * units + unit) * TC_GROUPS + g;
-      if (tile >= tiles) break;
-      const long long p_raw = tile * 128 + row;
-      const bool live = p_raw < P.total;
-      const long long p = live ? p_raw : P.total - 1;
-      const int n = (int)(p / P.M);
-      const float* xsrc = (c == 0) ? P.states_in : P.states_out;
-      float x[MMF_MAX_SD];
+      for (long long it = 0;; ++it) {
+        const long long tile = (it * units + unit) * G + g;
+        if (tile >= tiles) break;
+        const long long p_raw = tile * 128 + row;
+        const bool live = p_raw < P.total;
+        const long long p = live ? p_raw : P.total - 1;
+        const int n = (int)(p / P.M);
+        const float* xsrc = (c == 0) ? P.states_in : P.states_out;
+        float x[MMF_MAX_SD];
 #pragma unroll
-      for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
-      float* act_base = (P.act_out != nullptr && c > 0 && live)
-                            ? P.act_out + (size_t)(c - 1) * (L + 1) * P.total * U + (size_t)p * 4
-                            : nullptr;
-      const size_t act_plane = (size_t)P.total * U;
-      const size_t act_stride4 = (size_t)P.total * 4;
+        for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
 
-      // input layer on the CUDA cores -> A operand in the current half, published chunk by chunk
-      float2 xr[NCH * 8];
-      {
-        const uint32_t tbuf = tG + cur * 64 + col0;
-        const float4* b4 = reinterpret_cast<const float4*>(in_b + col0);
-        const float4* w4 = reinterpret_cast<const float4*>(in_Wt + col0);
-        float* act0 = act_base ? act_base + (size_t)(col0 / 4) * act_stride4 : nullptr;
+        // training: base of this particle's saved activations for head c (layer index selects the plane)
+        float* act_base = (TRAIN && P.act_out != nullptr && c > 0 && live)
+                              ? P.act_out + (size_t)(c - 1) * (L + 1) * P.total * U + (size_t)p * 4
+                              : nullptr;
+        const size_t act_plane = (size_t)P.total * U;
+        const size_t act_stride4 = (size_t)P.total * 4;
+
+        // ---- input layer on the CUDA cores: xr = relu(in_W x + in_b) -> A operand ------------------------
+        float2 xr[U / 2];
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(in_b);
+          const float4* w4 = reinterpret_cast<const float4*>(in_Wt);
 #pragma unroll
-        for (int chunk = 0; chunk < NCH; ++chunk) {
-          float2 v[8];
+          for (int chunk = 0; chunk < TC_CHUNKS; ++chunk) {
+            float2 v[8];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 t = b4[chunk * 4 + q4];
-            v[2 * q4] = make_float2(t.x, t.y);
-            v[2 * q4 + 1] = make_float2(t.z, t.w);
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 t = b4[chunk * 4 + q4];
+              v[2 * q4] = make_float2(t.x, t.y);
+              v[2 * q4 + 1] = make_float2(t.z, t.w);
+            }
+#pragma unroll
+            for (int i = 0; i < MMF_MAX_SD; ++i) {
+              if (i < sd) {
+                const float2 xi = make_float2(x[i], x[i]);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const float4 t = w4[i * (U / 4) + chunk * 4 + q4];
+                  v[2 * q4] = __ffma2_rn(make_float2(t.x, t.y), xi, v[2 * q4]);
+                  v[2 * q4 + 1] = __ffma2_rn(make_float2(t.z, t.w), xi, v[2 * q4 + 1]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j].x = fmaxf(v[j].x, 0.0f);
+              v[j].y = fmaxf(v[j].y, 0.0f);
+              xr[chunk * 8 + j] = v[j];
+            }
+            if (TRAIN && act_base != nullptr) store_act_chunk(act_base, chunk, v, act_stride4);
+            store_a_chunk<false>(v, tAhi, tAlo, chunk, single_pass);
           }
+        }
+
+        // ---- 64x64 layers ----------------------------------------------------------------------------------
+        for (int layer = 0; layer < L; ++layer) {
+          // hand the A operand to the issuer: my stores have retired and are ordered before the arrive it observes
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(abar + g);
+          float* arow = (TRAIN && act_base) ? act_base + (size_t)(layer + 1) * act_plane : nullptr;
+          if (layer == mid_at) {
+            const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
+            if (ch.mid_relu) epilogue_ws<EPI_MID_RELU, SPLIT>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4, my_dbar, dph);
+            else epilogue_ws<EPI_MID_LINEAR, SPLIT>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4, my_dbar, dph);
+          } else {
+            const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
+            const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U);
+            if ((rel & 1) == 0) epilogue_ws<EPI_RES_A, SPLIT>(tD, tAhi, tAlo, bsm, xr, single_pass, arow, act_stride4, my_dbar, dph);
+            else epilogue_ws<EPI_RES_B, SPLIT>(tD, tAhi, tAlo, bsm, xr, single_pass, arow, act_stride4, my_dbar, dph);
+          }
+        }
+        // ---- output layer -------------------------------------------------------------------------------------
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(abar + g);
+        mbar_wait(my_dbar, dph[0]);
+        dph[0] ^= 1;
+        tc_fence_after();
+        float y[MMF_MAX_SD + 1];
+        {
+          uint32_t d[16];
+          tmem_ld16(tD, d);
+          tc_wait_ld();
+#pragma unroll
+          for (int o = 0; o < MMF_MAX_SD + 1; ++o) y[o] = __uint_as_float(d[o]) + out_b[o];
+        }
+
+        if (c == 0) {
+          float gsel = 0.0f;
+#pragma unroll
+          for (int o = 0; o < MMF_MAX_SD + 1; ++o)
+            if (o == sd) gsel = y[o];
+          const float gate = 1.0f / (1.0f + expf(-gsel));
+          float e[MMF_MAX_SD];
+#pragma unroll
+          for (int i = 0; i < MMF_MAX_SD; ++i) e[i] = (i < sd) ? P.eps[p * sd + i] : 0.0f;
 #pragma unroll
           for (int i = 0; i < MMF_MAX_SD; ++i) {
             if (i < sd) {
-              const float2 xi = make_float2(x[i], x[i]);
+              float noise = 0.0f;
 #pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 t = w4[i * (U / 4) + chunk * 4 + q4];
-                v[2 * q4] = __ffma2_rn(make_float2(t.x, t.y), xi, v[2 * q4]);
-                v[2 * q4 + 1] = __ffma2_rn(make_float2(t.z, t.w), xi, v[2 * q4 + 1]);
-              }
+              for (int j = 0; j < MMF_MAX_SD; ++j)
+                if (j <= i && j < sd) noise = fmaf(P.q[i * sd + j], e[j], noise);
+              const float moved = (x[i] + y[i] * gate) + noise;
+              if (live) P.states_out[p * sd + i] = moved;
             }
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[j].x = fmaxf(v[j].x, 0.0f);
-            v[j].y = fmaxf(v[j].y, 0.0f);
-            xr[chunk * 8 + j] = v[j];
-          }
-          if (act0 != nullptr) store_act_chunk(act0, chunk, v, act_stride4);
-          if (chunk > 0) publish_chunk(my_cbar, chunk - 1);
-          store_a_chunk<false>(v, tbuf + chunk * 8, tbuf + chunk * 8 + 8, chunk, single_pass);
-        }
-        publish_chunk(my_cbar, NCH - 1);
-      }
-
-      for (int layer = 0; layer <= L; ++layer) {
-        mbar_wait(done + g, dphase, P.wait_hint_ns);
-        dphase ^= 1;
-        cur ^= 1;
-        tc_fence_after();
-        if (layer == L) break;
-        const uint32_t tbuf = tG + cur * 64 + col0;
-        float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane + (size_t)(col0 / 4) * act_stride4 : nullptr;
-        if (layer == mid_at) {
-          const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U + col0);
-          if (ch.mid_relu) epilogue_pipe<EPI_MID_RELU, NCH>(tbuf, brow, xr, single_pass, arow, act_stride4, my_cbar);
-          else epilogue_pipe<EPI_MID_LINEAR, NCH>(tbuf, brow, xr, single_pass, arow, act_stride4, my_cbar);
         } else {
-          const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
-          const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U + col0);
-          if ((rel & 1) == 0) epilogue_pipe<EPI_RES_A, NCH>(tbuf, bsm, xr, single_pass, arow, act_stride4, my_cbar);
-          else epilogue_pipe<EPI_RES_B, NCH>(tbuf, bsm, xr, single_pass, arow, act_stride4, my_cbar);
-        }
-      }
-
-      if (half != 0) continue;  // the second warp of a row pair has no part in the 16-column output layer
-      float y[MMF_MAX_SD + 1];
-      {
-        uint32_t d[16];
-        tmem_ld16(tG + cur * 64, d);
-        tc_wait_ld();
-#pragma unroll
-        for (int o = 0; o < MMF_MAX_SD + 1; ++o) y[o] = __uint_as_float(d[o]) + out_b[o];
-      }
-      if (c == 0) {
-        float gsel = 0.0f;
-#pragma unroll
-        for (int o = 0; o < MMF_MAX_SD + 1; ++o)
-          if (o == sd) gsel = y[o];
-        const float gate = 1.0f / (1.0f + expf(-gsel));
-        float e[MMF_MAX_SD];
-#pragma unroll
-        for (int i = 0; i < MMF_MAX_SD; ++i) e[i] = (i < sd) ? P.eps[p * sd + i] : 0.0f;
-#pragma unroll
-        for (int i = 0; i < MMF_MAX_SD; ++i) {
-          if (i < sd) {
-            float noise = 0.0f;
-#pragma unroll
-            for (int j = 0; j < MMF_MAX_SD; ++j)
-              if (j <= i && j < sd) noise = fmaf(P.q[i * sd + j], e[j], noise);
-            const float moved = (x[i] + y[i] * gate) + noise;
-            if (live) P.states_out[p * sd + i] = moved;
+          const float ll = y[0];
+          if (P.ll_out != nullptr && live) P.ll_out[(size_t)(c - 1) * P.total + p] = ll;
+          const float v = ll + (P.modw != nullptr ? __ldg(P.modw + (size_t)n * P.K + (c - 1)) : 0.0f);
+          float fused = v;
+          if (!first_head) {  // running log-sum-exp kept in logw_out between head phases
+            const float prev = P.logw_out[p];
+            const float mx = fmaxf(prev, v);
+            fused = (mx == -INFINITY) ? -INFINITY : mx + logf(expf(prev - mx) + expf(v - mx));
           }
+          if (live) P.logw_out[p] = last_head ? P.logw_in[p] + fused : fused;
         }
-      } else {
-        const float ll = y[0];
-        if (P.ll_out != nullptr && live) P.ll_out[(size_t)(c - 1) * P.total + p] = ll;
-        const float v = ll + (P.modw != nullptr ? __ldg(P.modw + (size_t)n * P.K + (c - 1)) : 0.0f);
-        float fused = v;
-        if (!first_head) {
-          const float prev = P.logw_out[p];
-          const float mx = fmaxf(prev, v);
-          fused = (mx == -INFINITY) ? -INFINITY : mx + logf(expf(prev - mx) + expf(v - mx));
-        }
-        if (live) P.logw_out[p] = last_head ? P.logw_in[p] + fused : fused;
+        // the next tile's input layer overwrites the A region: the out-layer MMA that read it has completed
       }
     }
+
   }
 
   tc_fence_before();
@@ -811,14 +783,23 @@ __global__ void __launch_bounds__(TC_GROUPS * (128 * TPR + 32), 1) k_particle_ch
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// Pipeline shape, fixed when the library is loaded (environment MMF_TC_VARIANT, read once: no getenv on the launch
+// path): 71 = warp-specialised, one issuer warp + 4 groups (default); 72 = same, layers issued as two N = 32 halves;
+// 73 = 3 groups; 41 / 31 = symmetric kernel, every group issues its own MMAs; 42 / 32 = symmetric, CTA pairs.
+static int tc_variant() {
+  static const int variant = [] {
+    const char* env = getenv("MMF_TC_VARIANT");
+    return env ? atoi(env) : 71;
+  }();
+  return variant;
+}
+
 int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
                              const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
                              int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream,
                              int first_chain, float* act_out) {
-  // pipeline shape: MMF_TC_VARIANT = <groups><cta group>: 41 = 4 groups, cta_group::1; 42 = 4 groups, CTA pairs
-  int variant = 41;
-  if (const char* env = getenv("MMF_TC_VARIANT")) variant = atoi(env);
-  const bool pair = (variant % 10) == 2;
+  const int variant = tc_variant();
+  const bool pair = variant < 70 && (variant % 10) == 2;
   TcParams P;
   P.K = model->num_heads;
   size_t cap = 0;
@@ -852,9 +833,6 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
   P.wait_hint_ns = 0;
   P.first_chain = first_chain;
   P.act_out = act_out;
-  P.stamps = getenv("MMF_TC_TIMESTAMPS") != nullptr;
-  P.use_lock = 0;
-  if (const char* env = getenv("MMF_TC_LOCK")) P.use_lock = atoi(env);
 
   const size_t smem = cap + 1024;  // + barriers, TMEM slot
   int sms = 148, dev = 0;
@@ -889,26 +867,31 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
     cfg.numAttrs = 1;                                                                             \
     MMF_CUDA(cudaLaunchKernelEx(&cfg, k_particle_chain_tc<G, PAIRED>, P));                        \
   } while (0)
-#define MMF_PIPE_LAUNCH(G, TPR)                                                                      \
+#define MMF_WS_LAUNCH(G, SPLIT)                                                                    \
   do {                                                                                            \
     static thread_local int configured_dev = -1;                                                  \
     static thread_local size_t window = 0;                                                        \
     if (configured_dev != dev) {                                                                  \
-      int rc = opt_in_shared_memory(k_particle_chain_pipe<G, TPR>, &window);                      \
+      int rc = opt_in_shared_memory(k_particle_chain_ws<G, SPLIT, false>, &window);               \
+      if (rc) return rc;                                                                          \
+      rc = opt_in_shared_memory(k_particle_chain_ws<G, SPLIT, true>, &window);                    \
       if (rc) return rc;                                                                          \
       configured_dev = dev;                                                                       \
     }                                                                                             \
     MMF_REQUIRE(smem <= window, "tensor-core chain needs %zu B of shared memory (window %zu B)", smem, window); \
     long long units = (tiles + G - 1) / G;                                                        \
     if (units > sms) units = sms;                                                                 \
-    k_particle_chain_pipe<G, TPR><<<(unsigned)units, G * (128 * TPR + 32), smem, stream>>>(P); \
-    MMF_LAUNCH_CHECK("k_particle_chain_pipe");                                                    \
+    if (act_out != nullptr)                                                                       \
+      k_particle_chain_ws<G, SPLIT, true><<<(unsigned)units, G * 128 + 128, smem, stream>>>(P);   \
+    else                                                                                          \
+      k_particle_chain_ws<G, SPLIT, false><<<(unsigned)units, G * 128 + 128, smem, stream>>>(P);  \
+    MMF_LAUNCH_CHECK("k_particle_chain_ws");                                                      \
     return MMF_OK;                                                                                \
   } while (0)
-  if (variant == 51) MMF_PIPE_LAUNCH(4, 1);
-  if (variant == 53) MMF_PIPE_LAUNCH(3, 1);
-  if (variant == 63) MMF_PIPE_LAUNCH(3, 2);
-#undef MMF_PIPE_LAUNCH
+  if (variant == 71) MMF_WS_LAUNCH(4, 1);
+  if (variant == 72) MMF_WS_LAUNCH(4, 2);
+  if (variant == 73) MMF_WS_LAUNCH(3, 1);
+#undef MMF_WS_LAUNCH
   switch (variant) {
     case 41: MMF_TC_LAUNCH(4, false); break;
     case 31: MMF_TC_LAUNCH(3, false); break;
@@ -922,16 +905,3 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
 }
 
 }  // namespace mmf
-
-// debug-only export (not part of the public ABI): copies the recorded phase timestamps to the host
-extern "C" int mmf_debug_tc_timestamps(unsigned long long* out, int max_entries) {
-  unsigned int count = 0;
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&count, mmf::g_tc_stamp_count, sizeof(count));
-  int n = (int)count < max_entries ? (int)count : max_entries;
-  if (n > 1600) n = 1600;
-  cudaMemcpyFromSymbol(out, mmf::g_tc_stamps, sizeof(unsigned long long) * 5 * n);
-  unsigned int zero = 0;
-  cudaMemcpyToSymbol(mmf::g_tc_stamp_count, &zero, sizeof(zero));
-  return n;
-}

@@ -4,8 +4,7 @@
 ref: crossmodal/push_models/layers.py:93-104, crossmodal/door_models/layers.py:43-63); only its forward
 changes: under ``torch.no_grad()`` on a CUDA device the Conv2d layers run through ``mmf_enc_trunk`` (one launch,
 tensor cores, bf16 hi/lo split operands, fp32 accumulation) and the Flatten/Linear tail stays with torch.  With autograd enabled (encoder training / pre-training) the plain module path runs, so
-gradients are untouched.  The trunk's scratch maps belong to the module instance and launches are ordered on the
-current stream: do not run the same encoder instance concurrently on two streams.  There is no CPU variant of the fused trunk: on a CPU tensor the module is the
+gradients are untouched.  The trunk's scratch maps are kept per (device, stream), so the same encoder instance may run on several streams.  There is no CPU variant of the fused trunk: on a CPU tensor the module is the
 ordinary torch Sequential, exactly as in the reference.
 """
 import torch
@@ -56,11 +55,16 @@ class ImageEncoder(nn.Sequential):
         return cache[1]
 
     def _scratch(self, device):
-        ws = self.__dict__.get("_mmf_ws")
-        if ws is None or ws[0] != str(device):
-            ws = (str(device), ops.enc_trunk_scratch(device))  # zeroed once: the kernels never write the guards
-            self.__dict__["_mmf_ws"] = ws
-        return ws[1]
+        """Scratch maps of the fused trunk, one set per (device, stream): launches on one stream are ordered, and two
+        streams running the same encoder instance never share maps.  Zeroed once: the kernels never write the guards."""
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+        cache = self.__dict__.setdefault("_mmf_ws", {})
+        ws = cache.get(key)
+        if ws is None:
+            if len(cache) >= 4:  # streams come and go: keep the footprint bounded
+                cache.clear()
+            ws = cache[key] = ops.enc_trunk_scratch(device)
+        return ws
 
     @staticmethod
     def _split_tail(tail):

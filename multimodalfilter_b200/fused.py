@@ -307,6 +307,11 @@ class PFPlan:
     def step(self, states, logw, controls, feats, modw, eps, *, precision, estimation, mode, alpha, M_out, uniforms,
              want_debug=False):
         self.refresh(states.device)
+        N = states.shape[0]
+        # upstream asserts len(controls) == N; here a mismatch would make the kernels index rows out of bounds
+        assert controls.shape[0] == N, f"controls have {controls.shape[0]} rows for {N} trajectories"
+        assert len(feats) == self.K and all(f is None or f.shape[0] == N for f in feats), "observation features / N mismatch"
+        assert modw is None or modw.shape[0] == N, "modality weights / N mismatch"
         rowbias = ops.pf_traj_rows(self.struct, self.K, controls, feats)
         res = ops.pf_predict_measure(self.struct, states, eps, rowbias, logw, modw, self.enabled_mask(),
                                      precision=precision, want_ll=want_debug)

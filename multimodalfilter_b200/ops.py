@@ -48,10 +48,10 @@ class _Profile:
     def run(self, name, kernels, fn, *args):
         self.launches += kernels
         if not self.enabled:
-            return fn(*args)
+            return _lib.call(fn, *args)
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        rc = fn(*args)
+        rc = _lib.call(fn, *args)
         stop.record()
         self._events.setdefault(name, []).append((start, stop))
         return rc
@@ -84,7 +84,7 @@ def pack_chain_mma(chain_struct, device):
     lib = _lib.load()
     nbytes = lib.mmf_chain_mma_bytes(C.byref(chain_struct))
     buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    _lib.check(lib.mmf_pack_chain_mma(C.byref(chain_struct), _lib.ptr(buf), _lib.stream_of(buf)))
+    _lib.check(_lib.call(lib.mmf_pack_chain_mma, C.byref(chain_struct), _lib.ptr(buf), _lib.stream_of(buf)))
     chain_struct.w_mma = buf.data_ptr()
     return buf
 
@@ -94,7 +94,7 @@ def pack_chain_bwd(chain_struct, device):
     lib = _lib.load()
     nbytes = lib.mmf_chain_bwd_bytes(C.byref(chain_struct))
     buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    _lib.check(lib.mmf_pack_chain_bwd(C.byref(chain_struct), _lib.ptr(buf), _lib.stream_of(buf)))
+    _lib.check(_lib.call(lib.mmf_pack_chain_bwd, C.byref(chain_struct), _lib.ptr(buf), _lib.stream_of(buf)))
     chain_struct.w_bwd = buf.data_ptr()
     return buf
 
@@ -113,6 +113,8 @@ def pf_heads_forward_train(model_struct, states, eps, rowbias, enabled_mask, pre
     N, M, sd = states.shape
     K, L = model_struct.num_heads, head_depth(model_struct)
     states, eps, rowbias = _f32c(states), _f32c(eps), _f32c(rowbias)
+    assert rowbias.shape == (1 + K, N, _lib.UNITS), f"rowbias {tuple(rowbias.shape)} != {(1 + K, N, _lib.UNITS)}"
+    assert eps.numel() == N * M * sd
     dev = states.device
     moved = torch.empty_like(states)
     ll = torch.full((K, N, M), float("nan"), device=dev, dtype=torch.float32)
@@ -302,6 +304,7 @@ def pf_predict_measure(model_struct, states, eps, rowbias, logw, modality_logw, 
     states, eps, rowbias, logw = _f32c(states), _f32c(eps), _f32c(rowbias), _f32c(logw)
     assert eps.numel() == N * M * sd and logw.shape == (N, M)
     K = model_struct.num_heads
+    assert rowbias.shape == (1 + K, N, _lib.UNITS), f"rowbias {tuple(rowbias.shape)} != {(1 + K, N, _lib.UNITS)}"
     if modality_logw is not None:
         modality_logw = _f32c(modality_logw)
         assert modality_logw.shape == (N, K), (modality_logw.shape, (N, K))
@@ -319,19 +322,16 @@ def pf_predict_measure(model_struct, states, eps, rowbias, logw, modality_logw, 
     return (states_out, logw_out, ll) if want_ll else (states_out, logw_out)
 
 
-_WORKSPACES = {}
-
-
 def _resample_workspace(N, M, device):
-    """Global scratch for trajectories that do not fit shared memory (cached per device, grown on demand)."""
-    need = _lib.load().mmf_pf_resample_workspace_bytes(N, M)
+    """Global scratch for trajectories that do not fit shared memory.  Allocated per call from torch's stream-ordered
+    caching allocator: two streams never share a slice, and during CUDA-graph capture the buffer comes from (and stays
+    alive in) the graph's private pool, so a replayed graph never writes into memory that has been handed to someone
+    else."""
+    with torch.cuda.device(device):
+        need = _lib.load().mmf_pf_resample_workspace_bytes(N, M)
     if need == 0:
         return None
-    buf = _WORKSPACES.get(device)
-    if buf is None or buf.numel() < need:
-        buf = torch.empty(need, dtype=torch.uint8, device=device)
-        _WORKSPACES[device] = buf
-    return buf
+    return torch.empty(need, dtype=torch.uint8, device=device)
 
 
 def pf_normalize_resample(states, logw_unnorm, *, estimation=ESTIMATE_WEIGHTED_AVERAGE, mode=RESAMPLE_NONE,

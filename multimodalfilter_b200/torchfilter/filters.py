@@ -17,6 +17,7 @@ Extensions beyond upstream (all optional, defaults reproduce upstream behaviour)
   ``precision``      "fp32" | "bf16x3" | "bf16" arithmetic of the per-particle MLP chain.
 """
 import math
+import warnings
 
 import torch
 
@@ -47,7 +48,9 @@ def _needs_grad(module, *tensors) -> bool:
 
 
 def _has_hooks(module) -> bool:
-    return bool(module._forward_hooks or module._forward_pre_hooks)
+    """Forward hooks on the filter or on any sub-module (dynamics, measurement heads, encoders...): the fused loop
+    never calls those modules' ``__call__``, so it must not be taken when somebody is listening."""
+    return any(m._forward_hooks or m._forward_pre_hooks for m in module.modules())
 
 
 class ParticleFilter(Filter):
@@ -84,12 +87,13 @@ class ParticleFilter(Filter):
 
     # ---- plan management -------------------------------------------------------------------------
     def fused_plan(self):
-        key = (id(self.dynamics_model), id(self.measurement_model))
+        # the cache holds the sub-modules themselves (compared by identity): a replaced module can never alias a
+        # stale plan through a recycled id()
         cached = self.__dict__.get("_mmf_plan")
-        if cached is None or cached[0] != key:
-            cached = (key, fused.PFPlan.build(self))
+        if cached is None or cached[0] is not self.dynamics_model or cached[1] is not self.measurement_model:
+            cached = (self.dynamics_model, self.measurement_model, fused.PFPlan.build(self))
             self.__dict__["_mmf_plan"] = cached
-        return cached[1]
+        return cached[2]
 
     # ---- random draws ------------------------------------------------------------------------------
     def _init_eps(self, M, N, sd, like):
@@ -348,10 +352,12 @@ class ParticleFilter(Filter):
                 # kernels recorded into the graph: they run at every replay, not during capture
                 st["launches"] = ops.PROFILE.launches - launches_before
                 ops.PROFILE.launches = launches_before
-            except Exception:  # capture is an optimisation: never let it take the eager path down with it
+            except Exception as exc:  # capture is an optimisation: never let it take the eager path down with it
                 self.particle_states, self.particle_log_weights = live
                 cache.update(graph=False, static=None)
                 torch.cuda.synchronize()
+                warnings.warn(f"forward_loop: CUDA-graph capture failed ({type(exc).__name__}: {exc}); "
+                              "this configuration keeps running with eager launches", RuntimeWarning)
                 return None
             self.particle_states, self.particle_log_weights = live
             cache.update(graph=graph, static=st)
@@ -441,10 +447,9 @@ class VirtualSensorExtendedKalmanFilter(ExtendedKalmanFilter):
         self.virtual_sensor_model = virtual_sensor_model
 
     def fused_plan(self):
-        key = id(self.dynamics_model)
         cached = self.__dict__.get("_mmf_plan")
-        if cached is None or cached[0] != key:
-            cached = (key, fused.EKFPlan.build([self]))
+        if cached is None or cached[0] is not self.dynamics_model:
+            cached = (self.dynamics_model, fused.EKFPlan.build([self]))
             self.__dict__["_mmf_plan"] = cached
         return cached[1]
 

@@ -71,6 +71,12 @@ class FusedHeads(torch.autograd.Function):
         rowbias = torch.cat([dyn_row[None], head_rows.detach()]).contiguous()
         moved, ll, act = ops.pf_heads_forward_train(plan.struct, states.detach(), eps, rowbias, enabled_mask,
                                                     precision=precision)
+        if enabled_mask != (1 << plan.K) - 1:
+            # planes of disabled heads are never written by the kernel: clear them here, once, so that backward can
+            # treat the saved tensor as read-only (retain_graph / a second backward see the same values)
+            for k in range(plan.K):
+                if not (enabled_mask >> k) & 1:
+                    act[k].zero_()
         ctx.plan, ctx.mask, ctx.shape = plan, enabled_mask, (N, M, sd)
         ctx.save_for_backward(act, moved)
         ctx.mark_non_differentiable(moved)
@@ -87,7 +93,6 @@ class FusedHeads(torch.autograd.Function):
             for k in range(plan.K):
                 if not (mask >> k) & 1:
                     delta[k].zero_()
-                    act[k].zero_()
         moved_flat = moved.reshape(N * M, sd)
         dW, db, g_in, g_out = ops.pf_heads_weight_grads(act, delta, moved_flat, d_ll.reshape(plan.K, N * M))
         d_rows = torch.zeros((plan.K, N, U), device=act.device, dtype=torch.float32)
