@@ -15,6 +15,10 @@ A "step" is ONE pass of the hot path over one batch of synthetic trajectories: t
                 stream: algorithmic FLOPs (189,824 / particle-step, hoisted
                 minimum) / launch time vs the measured bf16 peak of MEASURED_PEAKS.json.
   cpu_baseline  the oracle port (eager PyTorch, CPU, all host threads) on a bounded sample.
+  gpu_eager_baseline  the same oracle port with eager PyTorch on this B200 ("the reference on
+                this box" -- launch-bound, ~150-200 library kernels per filter step).
+  training      BASELINE config C4 at the same rank count: one BPTT step (forward over 15 filter steps, backward,
+                gradient all-reduce over NCCL, Adam) captured in ONE CUDA graph per rank; ms/step max over ranks.
 
 Multi-GPU: trajectories are sharded, N per rank is fixed (weak scaling), no data-path collective.
 """
@@ -42,11 +46,12 @@ WORKLOADS = {
            "Door task crossmodal EKF eval (state_dim=3), 256 trajectories x 100 steps"),
     "c4": ("PushCrossmodalParticleFilter", 2, 8192, 30, 15,
            "Push crossmodal PF BPTT training step (fwd+bwd, subsequence 16, 8192 trajectories), gradient allreduce"),
-    "c5": ("PushUnimodalParticleFilter", 2, 16384, 0, 2,
+    "c5": ("PushUnimodalParticleFilter", 2, 16384, 0, 10,
            "Particle-count sweep 1K-1M particles x 16K trajectories, trajectory-sharded"),
 }
 # bounded CPU sample (trajectories, steps) of the big workloads: a few seconds of host work per timed run
 CPU_SAMPLE = {"c3": (64, 20), "c4": (256, 15)}
+GPU_EAGER_SAMPLE = {"c3": (512, 20), "c1": (32, 50), "c2": (256, 100)}  # eager-torch oracle on the GPU (launch-bound)
 FLOP_PER_PARTICLE_STEP = {2: 189_824.0, 3: 190_336.0}  # BASELINE.md section 4 (hoisted minimum)
 
 
@@ -125,19 +130,22 @@ def build_inputs(workload, seed=0):
     return states, obs, controls
 
 
-def run_cpu_oracle(workload, n_sample, t_sample, repeats=1, warm=True):
-    """The reference's CPU path (oracle port: eager PyTorch on the host cores) on a bounded sample of
-    the workload.  Returns (particle-steps/s, description)."""
+def run_cpu_oracle(workload, n_sample, t_sample, repeats=1, warm=True, device="cpu"):
+    """The reference's path (oracle port: eager PyTorch, on the host cores or -- device="cuda:k" -- on the GPU) on a
+    bounded sample of the workload.  Returns (particle-steps/s, description, seconds)."""
     from multimodalfilter_b200.synthetic import fill_parameters, synthetic_trajectories
     from oracle import crossmodal_port as port
 
     name, sd, _, M, _, _ = WORKLOADS[workload]
-    filt = fill_parameters(getattr(port, name)(), seed=0).eval()
+    filt = fill_parameters(getattr(port, name)(), seed=0).eval().to(device)
     is_pf = hasattr(filt, "num_particles")
     if is_pf:
         filt.num_particles = M
     states, obs, controls = synthetic_trajectories(t_sample + 1, n_sample, sd, seed=0)
-    cov = (torch.eye(sd) * 0.1)[None].expand(n_sample, sd, sd)
+    states, controls = states.to(device), controls.to(device)
+    obs = {k: v.to(device) for k, v in obs.items()}
+    cov = (torch.eye(sd, device=device) * 0.1)[None].expand(n_sample, sd, sd)
+    on_gpu = str(device) != "cpu"
     best = None
     if warm:  # first call pays for thread-pool start-up, allocator growth and oneDNN primitive creation: not timed
         with torch.no_grad():
@@ -150,10 +158,13 @@ def run_cpu_oracle(workload, n_sample, t_sample, repeats=1, warm=True):
         with torch.no_grad():
             filt.initialize_beliefs(mean=states[0], covariance=cov)
             filt.forward_loop(observations={k: v[1:] for k, v in obs.items()}, controls=controls[1:])
+        if on_gpu:
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     units = n_sample * (M if is_pf else 1) * t_sample
-    sample = f"{name} oracle port, eager PyTorch CPU fp32, forward_loop incl. observation encoders, N={n_sample} M={M} T={t_sample}"
+    where = "GPU (eager, library kernels)" if on_gpu else "CPU"
+    sample = f"{name} oracle port, eager PyTorch {where} fp32, forward_loop incl. observation encoders, N={n_sample} M={M} T={t_sample}"
     return units / best, sample, best
 
 
@@ -185,35 +196,77 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def bptt_arm(args):
-    """BASELINE config C4: one BPTT training step = forward over 15 filter steps + backward + gradient
-    all-reduce + Adam, on N=8192 trajectories x 30 particles per GPU.  The observation encoders are hoisted and
-    frozen (their features are inputs, as in the primary timed region of the eval configs): at this batch size
-    the CNN activations a backward through them would have to keep do not fit any GPU (3 encoders x 8192 x 15
-    images x ~0.6 MB).  Trainable: both measurement heads, the observation halves of their first shared Linear,
-    and the modality weight model's fusion layers; the dynamics is frozen as in the reference's curricula."""
+def time_resample_modes(N, Mp, sd, dev, reps=12):
+    """mmf_pf_normalize_resample stand-alone at the workload's shape, every resampling mode: CUDA events around each
+    launch on the launching stream, L2 flushed (a 256 MB write) between launches, median.  Algorithmic bytes (BASELINE.md
+    section 4): log-weights read + written 8, states read + written 8 sd, float64 uniform 8 (multinomial only)."""
+    from multimodalfilter_b200 import _lib, ops
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    states = torch.randn(N, Mp, sd, device=dev, generator=g)
+    logw = torch.randn(N, Mp, device=dev, generator=g)  # log-normal weights, effective sample size ~ M / e
+    u_m = torch.rand(N, Mp, device=dev, dtype=torch.float64, generator=g)
+    u_s = torch.rand(N, device=dev, dtype=torch.float64, generator=g)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, mode, u in (("multinomial", _lib.RESAMPLE_MULTINOMIAL_STRICT, u_m), ("multinomial_fast", _lib.RESAMPLE_MULTINOMIAL_FAST, u_m),
+                          ("systematic", _lib.RESAMPLE_SYSTEMATIC_STRICT, u_s), ("systematic_fast", _lib.RESAMPLE_SYSTEMATIC_FAST, u_s)):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.pf_normalize_resample(states, logw, mode=mode, uniforms=u)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts[2:])[len(ts[2:]) // 2]
+        bytes_ = N * Mp * (8 + 8 * sd + (8 if u is u_m else 0))
+        out[name] = {"avg_launch_ms": ms, "achieved": bytes_ / (ms / 1e3) / 1e9, "unit": "GB/s", "bytes": bytes_}
+    return out
+
+
+def setup_ranks(args):
+    """One process per GPU (torch.distributed.run sets RANK / LOCAL_RANK / WORLD_SIZE); NCCL process group when N > 1."""
     import torch.distributed as dist
 
-    from multimodalfilter_b200 import _lib, ops
-    from multimodalfilter_b200.crossmodal import models as M_
-    from multimodalfilter_b200.distributed import allreduce_gradients, max_over_ranks
-    from multimodalfilter_b200.synthetic import fill_parameters
+    from multimodalfilter_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().mmf_device_check())
+    return world, rank, local_rank, dev
+
+
+def run_c4(ctx, steps, warmup, precision):
+    """BASELINE config C4: one BPTT training step = forward over 15 filter steps + backward + gradient all-reduce + Adam,
+    on N=8192 trajectories x 30 particles per GPU; the whole step (the NCCL all-reduce included: it is issued as
+    ncclAllReduce on the capture stream, multimodalfilter_b200.distributed.StreamAllReduce) is ONE CUDA graph per rank.
+    The observation encoders are hoisted and frozen (their features are inputs, as in the primary timed region of the eval
+    configs): at this batch size a backward through three CNNs x 8192 x 15 images would need ~220 GB of activations and is
+    the cuDNN-bound "next" row, not the recursion.  Trainable: both measurement heads, the observation halves of their
+    first shared Linear, and the modality weight model's fusion layers; the dynamics is frozen as in the reference's
+    curricula (ref: scripts/push_task/train_push.py:154,213).  Gradients live in one flat buffer (views), so the
+    collective is a single in-place all-reduce with no concatenate / copy-back.  Returns the result record."""
+    import torch.distributed as dist
+
+    from multimodalfilter_b200 import ops
+    from multimodalfilter_b200.crossmodal import models as M_
+    from multimodalfilter_b200.distributed import FlatGradients, StreamAllReduce, max_over_ranks
+    from multimodalfilter_b200.synthetic import fill_parameters
+
+    world, rank, local_rank, dev = ctx
     name, sd, N, Mp, T, cfg = WORKLOADS["c4"]
     filt = fill_parameters(M_.PushCrossmodalParticleFilter(), seed=0).to(dev)
     filt.train()
     filt.num_particles = Mp
-    filt.precision = args.precision or "bf16x3"
-    for p in filt.dynamics_model.parameters():
-        p.requires_grad_(False)
+    filt.precision = precision or "bf16x3"
     mm = filt.measurement_model
     wm = mm.crossmodal_weight_model
     trainable = [p for h in mm.measurement_models for p in list(h.state_layers.parameters()) + list(h.shared_layers.parameters())]
@@ -222,7 +275,9 @@ def bptt_arm(args):
         p.requires_grad_(False)
     for p in trainable:
         p.requires_grad_(True)
-    # fused: one multi-tensor kernel instead of ~10 launches per tensor; capturable: the step may live in a CUDA graph
+    grads = FlatGradients(trainable)
+    reduce_ = StreamAllReduce(dev)
+    # fused: one multi-tensor kernel instead of ~10 launches per tensor; capturable: the step lives in a CUDA graph
     opt = torch.optim.Adam(trainable, lr=1e-4, fused=True, capturable=True)
     g = torch.Generator(device=dev).manual_seed(rank)
     feats = [torch.randn(T, N, 64, device=dev, generator=g), torch.randn(T, N, 128, device=dev, generator=g)]
@@ -233,7 +288,7 @@ def bptt_arm(args):
     cov = (torch.eye(sd, device=dev) * 0.1)[None].expand(N, sd, sd).contiguous()
 
     def step():
-        opt.zero_grad(set_to_none=True)
+        grads.zero()
         filt.initialize_beliefs(mean=mean0, covariance=cov)
         ests = []
         for t in range(T):
@@ -241,7 +296,7 @@ def bptt_arm(args):
             ests.append(filt.forward(observations=None, controls=controls[t], _hoisted=([feats[0][t], feats[1][t]], modw)))
         loss = torch.mean((torch.stack(ests) - targets) ** 2)
         loss.backward()
-        allreduce_gradients(filt)
+        reduce_(grads.flat)  # the step's only collective, on this stream, between backward and Adam
         opt.step()
         return loss
 
@@ -251,87 +306,83 @@ def bptt_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    graph, static_loss, eager_ms = None, None, None
-    use_graph = world == 1 and not os.environ.get("MMF_BENCH_NO_GRAPH")
-    if not use_graph:
-        # multi-GPU (or MMF_BENCH_NO_GRAPH): eager steps on the default stream, NCCL all-reduce between backward and Adam.
-        # (capturing the NCCL all-reduce inside the step graph hung at 2 GPUs in round 1: not used.)
-        for _ in range(args.warmup):
+    graph, static_loss, eager_ms, launch = None, None, None, "eager"
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # every backward runs on `side`: autograd's AccumulateGrad nodes stay there
+        for _ in range(max(3, warmup)):  # also warms the NCCL communicator on this stream before any capture
             step()
-        barrier()
+        side.synchronize()
+        assert grads.intact(), "a parameter gradient left the flat buffer"
         ops.PROFILE.reset(enabled=True)
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk:
-            start.record()
-            for _ in range(args.steps):
-                loss = step()
-            stop.record()
-            barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step()
+        e1.record()
         prof = ops.PROFILE.collect()
         ops.PROFILE.reset(enabled=False)
-        for v in prof["kernels"].values():
-            v["total_ms"] /= args.steps
-        prof["launches"] //= args.steps
-    else:
-        # single GPU: warm-up on a side stream (as torch.cuda.graph wants it), one eager step with per-kernel events, then
-        # the whole training step -- forward, backward, Adam -- is captured in ONE CUDA graph and replayed: the eager
-        # step is bound by ~20 ms of Python / autograd dispatch for ~17 ms of kernels
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # every backward runs on `side`: autograd's AccumulateGrad nodes stay there
-            for _ in range(args.warmup):
-                step()
-            side.synchronize()
-            ops.PROFILE.reset(enabled=True)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            loss = step()
-            e1.record()
-            prof = ops.PROFILE.collect()
-            ops.PROFILE.reset(enabled=False)
-            eager_ms = e0.elapsed_time(e1)
+        eager_ms = e0.elapsed_time(e1)
+        if not os.environ.get("MMF_BENCH_NO_GRAPH"):
             try:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side):
                     static_loss = step()
                 graph.replay()  # first replay outside the timed region
                 side.synchronize()
+                launch = "one CUDA graph per training step (all-reduce inside)" if world > 1 else "one CUDA graph per training step"
             except Exception as exc:
-                # a failed capture leaves the generator / stream state unusable: start over without the graph
-                print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); restarting with eager steps",
+                print(f"[bench] rank {rank}: CUDA-graph capture of the training step failed ({type(exc).__name__}: {exc})",
                       file=sys.stderr, flush=True)
-                os.environ["MMF_BENCH_NO_GRAPH"] = "1"
-                os.execv(sys.executable, [sys.executable] + sys.argv)
-        torch.cuda.current_stream().wait_stream(side)
-        barrier()
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk, torch.cuda.stream(side):
-            start.record()
-            for _ in range(args.steps):
+                if world == 1:  # a failed capture leaves the generator / stream state unusable: start over without it
+                    os.environ["MMF_BENCH_NO_GRAPH"] = "1"
+                    os.execv(sys.executable, [sys.executable] + sys.argv)
+                raise
+    torch.cuda.current_stream().wait_stream(side)
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk, torch.cuda.stream(side):
+        start.record()
+        for _ in range(steps):
+            if graph is not None:
                 graph.replay()
+            else:
+                loss = step()
+        if graph is not None:
             loss = static_loss
-            stop.record()
-            side.synchronize()
-            barrier()
-    ms = max_over_ranks(start.elapsed_time(stop), dev) / args.steps
+        stop.record()
+        side.synchronize()
+        barrier()
+    ms = max_over_ranks(start.elapsed_time(stop), dev) / steps
     units = N * Mp * T
-    if rank == 0:
-        kern = {k: {"avg_ms": v["avg_ms"], "share": v["total_ms"] / ms} for k, v in prof["kernels"].items()}
-        line = {
-            "metric": "particle-steps/sec", "value": world * units / (ms / 1e3), "unit": "particle-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": filt.precision, "data": "synthetic",
-            "config": {"workload": cfg, "id": "c4", "model": name, "trajectories_per_gpu": N, "particles": Mp,
-                       "filter_steps_per_pass": T, "phases": "forward + backward + grad all-reduce + Adam",
-                       "encoders": "hoisted and frozen (features are inputs)", "final_loss": float(loss.detach()),
-                       "launch": "one CUDA graph per training step" if graph is not None else "eager",
-                       "eager_ms_per_step": eager_ms},
-            "clocks": clk.summary(), "gpu_launches": prof["launches"] * args.steps, "kernels": kern,
-            "e2e": {"value": world * units / (ms / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 4, "note": "training step is device-resident; loss scalar read back"},
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
+    kern = {k: {"avg_ms": v["avg_ms"], "share_of_eager_step": v["total_ms"] / eager_ms} for k, v in prof["kernels"].items()}
+    record = {
+        "metric": "particle-steps/sec", "value": world * units / (ms / 1e3), "unit": "particle-steps/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": filt.precision, "data": "synthetic",
+        "config": {"workload": cfg, "id": "c4", "model": name, "trajectories_per_gpu": N, "particles": Mp,
+                   "filter_steps_per_pass": T, "phases": "forward + backward + grad all-reduce + Adam",
+                   "encoders": "hoisted and frozen (features are inputs)", "final_loss": float(loss.detach()),
+                   "launch": launch, "eager_ms_per_step": eager_ms,
+                   "allreduce": {"elements": int(grads.flat.numel()), "bytes": int(grads.flat.numel()) * 4,
+                                 "ranks": world, "how": "ncclAllReduce (avg, fp32, in place on the flat gradient buffer) "
+                                                        "on the step's stream" if world > 1 else "none (1 rank)"}},
+        "clocks": clk.summary(), "gpu_launches": prof["launches"] * steps, "kernels": kern,
+        "e2e": {"value": world * units / (ms / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 4, "note": "training step is device-resident; loss scalar read back"},
+    }
+    reduce_.close()
+    del graph
+    return record
+
+
+def bptt_arm(args):
+    import torch.distributed as dist
+
+    ctx = setup_ranks(args)
+    record = run_c4(ctx, args.steps, args.warmup, args.precision)
+    if ctx[1] == 0:
+        print(json.dumps(record), flush=True)
+    if ctx[0] > 1:
         dist.destroy_process_group()
 
 
@@ -340,23 +391,16 @@ def sweep_arm(args):
     """BASELINE config C5: particle-count sweep M = 1K ... 1M at 16K trajectories (sharded over the ranks).
     16K x 1M particles do not fit one GPU (196 GB of state), so the trajectories are TILED (tile-of-trajectories outer,
     time inner: legal because trajectories are independent); a "step" here times a bounded number of tiles per M
-    (up to 2 tiles x 2 filter steps, a tile holds up to 134 M particles) and reports particle-steps/s per M -- tiles are independent
-    and identical, so the rate of the full 16K-trajectory sweep point is the same number.  value = geometric mean."""
+    (up to 2 tiles x 10 filter steps -- BASELINE.md's step count --, a tile holds up to 134 M particles) and reports
+    particle-steps/s per M -- tiles are independent and identical, so the rate of the full 16K-trajectory sweep point is
+    the same number.  value = geometric mean.  The trajectories are sharded over the ranks (strong scaling: 16K total)."""
     import torch.distributed as dist
 
     from multimodalfilter_b200 import _lib
     from multimodalfilter_b200.crossmodal import models as M_
     from multimodalfilter_b200.synthetic import fill_parameters
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.check(_lib.load().mmf_device_check())
+    world, rank, local_rank, dev = setup_ranks(args)
     name, sd, N_total, _, T, cfg = WORKLOADS["c5"]
     n_rank = N_total // world
     filt = fill_parameters(M_.MODEL_TYPES["push"][name](), seed=0).to(dev).eval()
@@ -367,7 +411,7 @@ def sweep_arm(args):
     points = []
     for Mp in (1024, 4096, 16384, 65536, 262144, 1048576):
         n_tile = max(1, min(n_rank, (1 << 27) // Mp))
-        tiles = min(2, max(1, n_rank // n_tile))
+        tiles = min(2 if Mp < 262144 else 1, max(1, n_rank // n_tile))
         filt.num_particles = Mp
         mean = torch.randn(n_tile, sd, device=dev, generator=g)
         cov = (torch.eye(sd, device=dev) * 0.1)[None].expand(n_tile, sd, sd).contiguous()
@@ -444,15 +488,8 @@ def main():
     from multimodalfilter_b200.crossmodal import models as M_
     from multimodalfilter_b200.synthetic import fill_parameters
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.check(_lib.load().mmf_device_check())
+    ctx = setup_ranks(args)
+    world, rank, local_rank, dev = ctx
 
     name, sd, N, Mp, T, cfg = WORKLOADS[args.workload]
     task = "push" if name.startswith("Push") else "door"
@@ -549,8 +586,13 @@ def main():
     # inputs per pass (>= 100 MB of particle state + features) exceed nothing like L2 reuse across passes:
     # every step rewrites the N*M particle set (C3: 49 MB states+weights per step, new noise each step).
     ms_resident, clocks, prof = timed(resident_pass, args.steps, args.warmup, profile=True)
-    # small workloads capture their CUDA graph on the second call: keep that out of the timed region
-    ms_e2e, clocks_e2e, _ = timed(e2e_pass, max(1, min(args.steps, 3)), 1 if args.workload == "c3" else 3)
+    # same step / warm-up counts as `value` (small workloads capture their CUDA graph on the second call: warm-up)
+    ms_e2e, clocks_e2e, _ = timed(e2e_pass, args.steps, args.warmup)
+
+    # ---- the HBM-bound kernel of the step, stand-alone, per resampling mode (north star: >= 60 % of the HBM roofline) ----
+    hbm_modes = None
+    if is_pf and args.workload == "c3":
+        hbm_modes = time_resample_modes(N, Mp, sd, dev)
 
     value = world * units_per_pass / (ms_resident / 1e3)
     e2e_value = world * units_per_pass / (ms_e2e / 1e3)
@@ -571,8 +613,17 @@ def main():
         "gpu_launches": prof["launches"] if prof else 0,
     }
 
+    # ---- BASELINE config C4 at the same rank count: the path's only collective (gradient all-reduce) ----------------
+    if args.workload == "c3" and not os.environ.get("MMF_BENCH_NO_TRAINING"):
+        del feats, modw
+        filt.particle_states = filt.particle_log_weights = None
+        torch.cuda.empty_cache()
+        tr = run_c4(ctx, max(args.steps, 5), args.warmup, args.precision)
+        line["training"] = {k: tr[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "steps", "dtype", "config", "clocks")}
+        line["training"]["kernels"] = tr["kernels"]
     if rank == 0:
         peaks = measured_peaks()
+        line["config"]["e2e_timing"] = "same steps / warm-up as value"
         if is_pf and prof and prof["kernels"].get("pf_predict_measure"):
             k = prof["kernels"]["pf_predict_measure"]
             flops = FLOP_PER_PARTICLE_STEP[sd] * N * Mp
@@ -588,11 +639,16 @@ def main():
             }
             nr = prof["kernels"].get("pf_normalize_resample")
             if nr:
-                bytes_ = N * Mp * (8 + 8 * sd + 8)  # logw r/w, states r/w, fp64 uniform
+                systematic = args.resample_mode.startswith("systematic")
+                bytes_ = N * Mp * (8 + 8 * sd + (0 if systematic else 8))  # logw r/w, states r/w, fp64 uniform
                 line["roofline"]["hbm_kernel"] = {
-                    "kernel": "k_normalize_resample", "bound": "hbm", "achieved": bytes_ / (nr["avg_ms"] / 1e3) / 1e9,
-                    "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": bytes_ / (nr["avg_ms"] / 1e3) / 1e9 / peaks["hbm_gbs"]}
+                    "kernel": "mmf_pf_normalize_resample inside the step", "mode": args.resample_mode, "bound": "hbm",
+                    "achieved": bytes_ / (nr["avg_ms"] / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": bytes_ / (nr["avg_ms"] / 1e3) / 1e9 / peaks["hbm_gbs"], "avg_launch_ms": nr["avg_ms"]}
+                if hbm_modes:
+                    for m in hbm_modes.values():
+                        m["frac"] = m["achieved"] / peaks["hbm_gbs"]
+                    line["roofline"]["hbm_kernel"]["standalone_by_mode"] = hbm_modes
         elif prof and prof["kernels"].get("ekf_loop"):
             k = prof["kernels"]["ekf_loop"]
             bytes_ = 340.0 * N * T  # 340 B / trajectory-step (K=2, sd=3)
@@ -607,6 +663,16 @@ def main():
             rate, sample, dt = run_cpu_oracle(args.workload, n_s, t_s)
             line["cpu_baseline"] = {"value": rate, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "sample": sample, "seconds": dt}
+            if world == 1:
+                # the oracle with eager torch on this B200 -- "the reference on this box"
+                try:
+                    n_g, t_g = GPU_EAGER_SAMPLE.get(args.workload, (min(N, 256), min(T, 50)))
+                    rate, sample, dt = run_cpu_oracle(args.workload, n_g, t_g, device=str(dev))
+                    line["gpu_eager_baseline"] = {"value": rate, "unit": "particle-steps/s", "kind": "port", "sample": sample,
+                                                  "seconds": dt, "speedup_e2e": e2e_value / rate}
+                except Exception as exc:  # the oracle is test infrastructure: never let it take the bench line down
+                    line["gpu_eager_baseline"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

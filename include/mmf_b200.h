@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MMF_ABI_VERSION 1
+#define MMF_ABI_VERSION 2
 #define MMF_UNITS 64
 #define MMF_MAX_SD 4
 #define MMF_MAX_CD 16
@@ -145,6 +145,22 @@ int mmf_pf_predict_measure(const mmf_pf_model* model, int32_t N, int32_t M, cons
                            const float* modality_logw, uint32_t enabled_mask, int32_t precision,
                            float* states_out, float* logw_unnorm_out, float* ll_out, void* stream);
 
+/* R1: the whole T-step recursion of a recognised particle filter, enqueued by ONE call (replaces the Python loop of
+ * A.2 `Filter.forward_loop` over A.3 `ParticleFilter.forward`; call site ref: crossmodal/eval_helpers.py:139-142).
+ * The observation encoders are hoisted: `obs_feats[k]` is (T, N, F_k) (NULL for a disabled head), `modality_logw`
+ * (T, N, K) or NULL, `controls` (T, N, cd), `eps` (T, N*M, sd) process noise, `uniforms` float64 (T, N, M)
+ * [multinomial*] / (T, N) [systematic*] / NULL [MMF_RESAMPLE_NONE].  Hard resampling that keeps the particle count.
+ *   states (N, M, sd), logw (N, M): IN the particle set entering step 0, OUT the set after step T-1;
+ *   est_out (T, N, sd): the state estimate of every step;
+ *   workspaces (caller-owned): rowbias_ws (1+K, T*N, 64) floats, states_ws (N, M, sd), logw_ws (N, M),
+ *   resample_ws of mmf_pf_resample_workspace_bytes(N, M) bytes (may be NULL when that is 0).
+ * Launches: 1 (per-trajectory rows of all T steps) + 2 per step (per-particle chain, normalise/estimate/resample). */
+int mmf_pf_forward_loop(const mmf_pf_model* model, int32_t T, int32_t N, int32_t M, float* states, float* logw,
+                        const float* controls, const float* const* obs_feats, const float* modality_logw,
+                        uint32_t enabled_mask, int32_t precision, const float* eps, int32_t estimation_method,
+                        int32_t resample_mode, const double* uniforms, float* rowbias_ws, float* states_ws,
+                        float* logw_ws, float* est_out, void* resample_ws, void* stream);
+
 /* Second half of R6, and R7 (A.3): per trajectory
  *   logw = logw_unnorm - logsumexp_m(logw_unnorm);  est = sum_m exp(logw) x  (or argmax particle)
  *   resample_mode != NONE: logits = logw (alpha == 1) or log(alpha e^logw + (1-alpha)/M);
@@ -259,14 +275,17 @@ int mmf_enc_conv3x3(int32_t n_images, int32_t cin, int32_t cout, const void* in_
 
 /* Parameter gradients of the heads from the saved activations and the deltas (both (K, L+1, 16, rows, 4)
  * chunk-major planes: element [k][l][c][p][j] = column 4c+j of row p), fp32 reductions over the N*M rows:
- *   dW_out   (K, L, 64, 64)  += delta[k][l]^T act[k][l]              the L 64x64 layers
- *   db_out   (K, L+1, 64)    += column sums of delta[k][l]           (plane L = the input layer)
- *   g_in_out (K, 64, sd)     += delta[k][L]^T x,  x = states (rows, sd)   input-layer weight
- *   g_out_out(K, 64)         += act[k][L]^T d_ll[k],  d_ll (K, rows)      output-layer weight
- * All outputs must be zero-initialised by the caller (partial sums are combined atomically). */
+ *   dW_out   (K, L, 64, 64)  = delta[k][l]^T act[k][l]               the L 64x64 layers
+ *   db_out   (K, L+1, 64)    = column sums of delta[k][l]            (plane L = the input layer)
+ *   g_in_out (K, 64, sd)     = delta[k][L]^T x,  x = states (rows, sd)    input-layer weight
+ *   g_out_out(K, 64)         = act[k][L]^T d_ll[k],  d_ll (K, rows)       output-layer weight
+ * The outputs are OVERWRITTEN.  The rows are split over CTAs that write partial sums into `workspace`
+ * (mmf_pf_heads_weight_grads_workspace_bytes() bytes, 16-byte aligned, caller-owned); a second kernel adds the
+ * partials in a fixed order: no floating-point atomics, the gradients are bit-reproducible from run to run. */
+size_t mmf_pf_heads_weight_grads_workspace_bytes(int32_t K, int32_t L, int64_t rows);
 int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, int32_t sd, const float* act, const float* delta,
                               const float* x, const float* d_ll, float* dW_out, float* db_out, float* g_in_out,
-                              float* g_out_out, void* stream);
+                              float* g_out_out, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

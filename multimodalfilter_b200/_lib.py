@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmf_b200.so")
 
 MAX_SD, MAX_CD, MAX_HEADS, UNITS = 4, 16, 4, 64
+ABI_VERSION = 2
 
 RESAMPLE_NONE = 0
 RESAMPLE_MULTINOMIAL_STRICT = 1
@@ -85,6 +86,11 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(PFModel), _i32, _i32, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp],
     ),
+    "mmf_pf_forward_loop": (
+        C.c_int,
+        [C.POINTER(PFModel), _i32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_vp), _vp, _u32, _i32, _vp, _i32, _i32, _vp, _vp,
+         _vp, _vp, _vp, _vp, _vp],
+    ),
     "mmf_pf_resample_workspace_bytes": (_sz, [_i32, _i32]),
     "mmf_pf_normalize_resample": (
         C.c_int,
@@ -101,7 +107,8 @@ PROTOTYPES = {
     "mmf_pf_heads_forward_train": (
         C.c_int, [C.POINTER(PFModel), _i32, _i32, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp]),
     "mmf_pf_heads_backward": (C.c_int, [C.POINTER(PFModel), _i32, _i32, _vp, _vp, _u32, _vp, _vp]),
-    "mmf_pf_heads_weight_grads": (C.c_int, [_i32, _i32, C.c_int64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_pf_heads_weight_grads_workspace_bytes": (_sz, [_i32, _i32, C.c_int64]),
+    "mmf_pf_heads_weight_grads": (C.c_int, [_i32, _i32, C.c_int64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmf_enc_map_bytes": (_sz, [_i32]),
     "mmf_enc_trunk_scratch_bytes": (_sz, []),
     "mmf_enc_trunk_weight_bytes": (_sz, []),
@@ -131,8 +138,8 @@ def load():
             fn = getattr(lib, name)
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.mmf_abi_version() != 1:
-            raise MMFError(f"ABI mismatch: library reports version {lib.mmf_abi_version()}, binding expects 1")
+        if lib.mmf_abi_version() != ABI_VERSION:
+            raise MMFError(f"ABI mismatch: library reports version {lib.mmf_abi_version()}, binding expects {ABI_VERSION}")
         _lib = lib
     return _lib
 

@@ -112,6 +112,65 @@ int mmf_pf_predict_measure(const mmf_pf_model* model, int32_t N, int32_t M, cons
   return MMF_E_INVALID;
 }
 
+int mmf_pf_forward_loop(const mmf_pf_model* model, int32_t T, int32_t N, int32_t M, float* states, float* logw,
+                        const float* controls, const float* const* obs_feats, const float* modality_logw,
+                        uint32_t enabled_mask, int32_t precision, const float* eps, int32_t estimation_method,
+                        int32_t resample_mode, const double* uniforms, float* rowbias_ws, float* states_ws,
+                        float* logw_ws, float* est_out, void* resample_ws, void* stream_) {
+  int rc = validate_pf_model(model);
+  if (rc) return rc;
+  MMF_REQUIRE(T >= 0 && N >= 0 && M >= 1, "forward_loop: bad shape T=%d N=%d M=%d", T, N, M);
+  if (T == 0 || N == 0) return MMF_OK;
+  MMF_REQUIRE(states && logw && controls && obs_feats && eps && rowbias_ws && states_ws && logw_ws && est_out,
+              "forward_loop: NULL buffer");
+  MMF_REQUIRE(estimation_method == MMF_ESTIMATE_WEIGHTED_AVERAGE || estimation_method == MMF_ESTIMATE_ARGMAX,
+              "forward_loop: unknown estimation method %d", estimation_method);
+  MMF_REQUIRE(resample_mode >= MMF_RESAMPLE_NONE && resample_mode <= MMF_RESAMPLE_SYSTEMATIC_FAST,
+              "forward_loop: unknown resample mode %d", resample_mode);
+  MMF_REQUIRE(resample_mode == MMF_RESAMPLE_NONE || uniforms != nullptr, "forward_loop: resampling needs uniforms");
+  MMF_REQUIRE(precision >= MMF_PREC_FP32 && precision <= MMF_PREC_BF16, "forward_loop: unknown precision mode %d", precision);
+  MMF_REQUIRE((long long)T * N <= 0x7fffffffLL, "forward_loop: T * N = %lld rows exceed the hoisting kernel's range",
+              (long long)T * N);
+  const uint32_t all = (1u << model->num_heads) - 1u;
+  MMF_REQUIRE((enabled_mask & all) != 0, "forward_loop: no measurement head enabled (mask 0x%x)", enabled_mask);
+  enabled_mask &= all;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int sd = model->state_dim, K = model->num_heads;
+  const bool systematic = resample_mode == MMF_RESAMPLE_SYSTEMATIC_STRICT || resample_mode == MMF_RESAMPLE_SYSTEMATIC_FAST;
+  // the per-trajectory rows of ALL steps in one launch: they do not depend on the particles
+  rc = launch_traj_rows(model, T * N, controls, obs_feats, rowbias_ws, stream);
+  if (rc) return rc;
+  const size_t NM = (size_t)N * M;
+  float* cur = states;     // particle set entering the step
+  float* moved = states_ws;  // particle set after the dynamics (and, without resampling, after the step)
+  for (int t = 0; t < T; ++t) {
+    const float* rb = rowbias_ws + (size_t)t * N * MMF_UNITS;
+    const float* mw = modality_logw ? modality_logw + (size_t)t * N * K : nullptr;
+    const float* e = eps + (size_t)t * NM * sd;
+    if (precision == MMF_PREC_FP32)
+      rc = launch_particle_chain_ffma(model, N, M, cur, e, rb, logw, mw, enabled_mask, moved, logw_ws, nullptr, stream, T * N);
+    else
+      rc = launch_particle_chain_tc(model, N, M, cur, e, rb, logw, mw, enabled_mask, precision, moved, logw_ws, nullptr,
+                                    stream, 0, nullptr, T * N);
+    if (rc) return rc;
+    ResampleParams P;
+    P.N = N; P.M = M; P.sd = sd; P.M_out = M;
+    P.estimation = estimation_method; P.mode = resample_mode; P.alpha = 1.0f;
+    P.states = moved; P.logw_unnorm = logw_ws; P.logits_in = nullptr;
+    P.uniforms = uniforms ? uniforms + (size_t)t * (systematic ? (size_t)N : NM) : nullptr;
+    P.states_out = resample_mode == MMF_RESAMPLE_NONE ? nullptr : cur;  // `cur` is dead once the chain kernel has read it
+    P.logw_out = logw; P.est_out = est_out + (size_t)t * N * sd;
+    P.logw_norm_out = nullptr; P.logits_out = nullptr; P.idx_out = nullptr;
+    rc = launch_normalize_resample(P, resample_ws, stream);
+    if (rc) return rc;
+    if (resample_mode == MMF_RESAMPLE_NONE) {  // the moved set IS the next step's input: swap the roles of the buffers
+      float* tmp = cur; cur = moved; moved = tmp;
+    }
+  }
+  if (cur != states) MMF_CUDA(cudaMemcpyAsync(states, cur, NM * sd * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  return MMF_OK;
+}
+
 size_t mmf_pf_resample_workspace_bytes(int32_t N, int32_t M) {
   if (N <= 0 || M <= 0) return 0;
   return resample_workspace_bytes(N, M);
@@ -273,14 +332,20 @@ int mmf_pf_heads_backward(const mmf_pf_model* model, int32_t N, int32_t M, const
   return launch_head_chain_bwd(model, N, M, act, d_ll, enabled_mask & all, delta_out, (cudaStream_t)stream);
 }
 
+size_t mmf_pf_heads_weight_grads_workspace_bytes(int32_t K, int32_t L, int64_t rows) {
+  if (K < 1 || K > MMF_MAX_HEADS || L < 1 || rows <= 0) return 0;
+  return heads_dw_workspace_bytes(K, L, rows);
+}
+
 int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, int32_t sd, const float* act, const float* delta,
                               const float* x, const float* d_ll, float* dW_out, float* db_out, float* g_in_out,
-                              float* g_out_out, void* stream) {
+                              float* g_out_out, void* workspace, void* stream) {
   MMF_REQUIRE(K >= 1 && K <= MMF_MAX_HEADS && L >= 1 && rows >= 0 && sd >= 1 && sd <= MMF_MAX_SD,
               "heads_weight_grads: bad shape K=%d L=%d sd=%d", K, L, sd);
   MMF_REQUIRE(rows == 0 || (act && delta && x && d_ll && dW_out && db_out && g_in_out && g_out_out),
               "heads_weight_grads: NULL buffer");
-  return launch_heads_dw(K, L, rows, sd, act, delta, x, d_ll, dW_out, db_out, g_in_out, g_out_out, (cudaStream_t)stream);
+  return launch_heads_dw(K, L, rows, sd, act, delta, x, d_ll, dW_out, db_out, g_in_out, g_out_out, workspace,
+                         (cudaStream_t)stream);
 }
 
 size_t mmf_enc_map_bytes(int32_t channels) { return enc_map_bytes_host(channels); }

@@ -1027,8 +1027,10 @@ int launch_enc_trunk(int n_images, int cout, const float* images, const void* we
   //       groups; as built the epilogue is the limiter and it lands at 4.9 ms, level with variant 0 on the same box
   // (TS-form variants -- A through a TMEM ring filled by gather warps, 5.5-5.7 ms -- were measured and removed, see
   //  DESIGN.md section 3.2 and the git history.)
-  int variant = 0;
-  if (const char* env = getenv("MMF_ENC_VARIANT")) variant = atoi(env);
+  static const int variant = [] {  // read once when first used: no getenv on the launch path
+    const char* env = getenv("MMF_ENC_VARIANT");
+    return env ? atoi(env) : 0;
+  }();
   if (variant == 3) k_enc_trunk_dx<<<grid, DX_THREADS, smem, stream>>>(P);
   else k_enc_trunk<<<grid, ENC_THREADS, smem, stream>>>(P);
   MMF_LAUNCH_CHECK("k_enc_trunk");

@@ -39,11 +39,12 @@ struct EkfParams {
 
 int launch_particle_chain_ffma(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
                                const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
-                               float* states_out, float* logw_out, float* ll_out, cudaStream_t stream);
+                               float* states_out, float* logw_out, float* ll_out, cudaStream_t stream,
+                               int rb_stride = 0);
 int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
                              const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
                              int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream,
-                             int first_chain = 0, float* act_out = nullptr);
+                             int first_chain = 0, float* act_out = nullptr, int rb_stride = 0);
 int launch_traj_rows(const mmf_pf_model* model, int N, const float* controls, const float* const* obs_feats,
                      float* out, cudaStream_t stream);
 int launch_fuse_loglik(int N, int M, int K, const float* ll, const float* w, float* out, cudaStream_t stream);
@@ -58,8 +59,10 @@ size_t chain_bwd_bytes(const mmf_chain* chain);
 int pack_chain_bwd(const mmf_chain* chain, void* dst, cudaStream_t stream);
 int launch_head_chain_bwd(const mmf_pf_model* model, int N, int M, const float* act, const float* d_ll, uint32_t enabled,
                           float* delta_out, cudaStream_t stream);
+size_t heads_dw_workspace_bytes(int K, int L, long long P);
 int launch_heads_dw(int K, int L, long long P, int sd, const float* act, const float* delta, const float* x,
-                    const float* d_ll, float* dW, float* db, float* g_in, float* g_out, cudaStream_t stream);
+                    const float* d_ll, float* dW, float* db, float* g_in, float* g_out, void* workspace,
+                    cudaStream_t stream);
 size_t enc_map_bytes_host(int channels);
 size_t enc_trunk_weight_bytes();
 size_t enc_trunk_scratch_bytes();

@@ -307,89 +307,10 @@ int launch_head_chain_bwd(const mmf_pf_model* model, int N, int M, const float* 
 }  // namespace mmf
 
 // ---- weight gradients: dW[k][l] = delta[k][l]^T act[k][l]  (64 x 64, reduction over the N*M rows) ----------------
-// HBM-bound (2 x 256 B per row per layer against 4096 FMAs): a register-tiled fp32 kernel on the CUDA cores keeps
-// up with the memory system, so the reduction is done in full fp32.  Split over row chunks; partial 64x64 tiles
-// are combined with fp32 atomics into the zero-initialised output.
+// HBM-bound (2 x 256 B per row per layer against 4096 FMAs).  The rows are split over CTAs; every CTA writes its partial
+// 64 x 64 tile (and partial column sums) to a workspace and a second kernel adds the partials IN A FIXED ORDER, so the
+// gradients are bit-reproducible from run to run (hard part 4: no floating-point atomics).
 namespace mmf {
-
-constexpr int DW_ROWS = 32;      // rows staged per iteration
-constexpr int DW_THREADS = 256;  // each thread owns a 4 x 4 block of the 64 x 64 output
-
-__global__ void __launch_bounds__(DW_THREADS) k_heads_dw(const float* __restrict__ act, const float* __restrict__ delta,
-                                                         float* __restrict__ dW, float* __restrict__ db, long long P,
-                                                         int planes_per_head, int L, int rows_per_cta) {
-  __shared__ __align__(16) float sa[DW_ROWS][U + 4];  // +4: rows 4 banks apart for the column-chunk-wise staging stores
-  __shared__ __align__(16) float sd[DW_ROWS][U + 4];
-  const int layer = blockIdx.y, head = blockIdx.z;
-  const size_t plane = ((size_t)head * planes_per_head + layer) * (size_t)P * U;
-  const float* A = act + plane;
-  const float* D = delta + plane;
-  const long long row0 = (long long)blockIdx.x * rows_per_cta;
-  const long long row1 = row0 + rows_per_cta < P ? row0 + rows_per_cta : P;
-  const int tid = threadIdx.x;
-  const int jo = (tid >> 4) * 4;  // output-feature block (rows of dW)
-  const int io = (tid & 15) * 4;  // input-feature block  (cols of dW)
-  float2 acc[4][2];  // packed fp32x2 accumulators: acc[a][h] = columns io + 2h, io + 2h + 1 of row jo + a
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) acc[a][h] = make_float2(0.0f, 0.0f);
-  float colsum = 0.0f;  // bias gradient of column `tid` (threads 0..63): sum of delta over the rows
-
-  // 32 rows x 64 floats = 512 float4 per operand = 2 per thread; a warp reads 32 consecutive rows of one column chunk
-  // (chunk-major planes).  The loads of tile t+1 are issued before tile t is consumed (register double buffer).
-  float4 va[2], vd[2];
-  auto fetch = [&](long long r) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * DW_THREADS;
-      const int c4 = e >> 5, rr = e & 31;
-      const bool ok = r + rr < row1;
-      const size_t off = ((size_t)c4 * P + (size_t)(r + rr)) * 4;
-      va[q] = ok ? __ldg(reinterpret_cast<const float4*>(A + off)) : make_float4(0, 0, 0, 0);
-      vd[q] = ok ? __ldg(reinterpret_cast<const float4*>(D + off)) : make_float4(0, 0, 0, 0);
-    }
-  };
-  if (row0 < row1) fetch(row0);
-  for (long long r = row0; r < row1; r += DW_ROWS) {
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * DW_THREADS;
-      const int c4 = e >> 5, rr = e & 31;
-      reinterpret_cast<float4*>(&sa[rr][0])[c4] = va[q];
-      reinterpret_cast<float4*>(&sd[rr][0])[c4] = vd[q];
-    }
-    __syncthreads();
-    if (r + DW_ROWS < row1) fetch(r + DW_ROWS);
-    if (tid < U) {
-#pragma unroll 8
-      for (int rr = 0; rr < DW_ROWS; ++rr) colsum += sd[rr][tid];
-    }
-#pragma unroll 8
-    for (int rr = 0; rr < DW_ROWS; ++rr) {
-      const float4 dv = *reinterpret_cast<const float4*>(&sd[rr][jo]);
-      const float4 av = *reinterpret_cast<const float4*>(&sa[rr][io]);
-      const float dj[4] = {dv.x, dv.y, dv.z, dv.w};
-      const float2 a01 = make_float2(av.x, av.y), a23 = make_float2(av.z, av.w);
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {  // FFMA2: two FMAs per issue slot
-        const float2 d2 = make_float2(dj[a], dj[a]);
-        acc[a][0] = __ffma2_rn(d2, a01, acc[a][0]);
-        acc[a][1] = __ffma2_rn(d2, a23, acc[a][1]);
-      }
-    }
-  }
-  float* out = dW + ((size_t)head * L + layer) * U * U;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    atomicAdd(out + (size_t)(jo + a) * U + io + 0, acc[a][0].x);
-    atomicAdd(out + (size_t)(jo + a) * U + io + 1, acc[a][0].y);
-    atomicAdd(out + (size_t)(jo + a) * U + io + 2, acc[a][1].x);
-    atomicAdd(out + (size_t)(jo + a) * U + io + 3, acc[a][1].y);
-  }
-  if (tid < U) atomicAdd(db + ((size_t)head * planes_per_head + layer) * U + tid, colsum);
-}
 
 // ---- dW on the tensor cores -----------------------------------------------------------------------------------
 // dW = delta^T act is a (64 x rows) x (rows x 64) contraction with the ROWS as K.  Both operands are "MN-major" for
@@ -440,9 +361,11 @@ __device__ __forceinline__ void split8_rn(const float4& x0, const float4& x1, ui
   lo4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// part_dW: [head][layer][chunk][64][64], part_db: [head][layer][chunk][64]   (chunk = blockIdx.x)
 __global__ void __launch_bounds__(DWT_THREADS, 1) k_heads_dw_tc(const float* __restrict__ act, const float* __restrict__ delta,
-                                                                float* __restrict__ dW, float* __restrict__ db, long long P,
-                                                                int planes_per_head, int L, int rows_per_cta) {
+                                                                float* __restrict__ part_dW, float* __restrict__ part_db,
+                                                                long long P, int planes_per_head, int L, int rows_per_cta) {
+  __shared__ float s_colsum[DWT_THREADS / 32][2][8];
   extern __shared__ __align__(1024) uint8_t smem[];  // [buffer 0: A | B][buffer 1: A | B] + barriers
   uint64_t* done = reinterpret_cast<uint64_t*>(smem + 4 * DWT_OPERAND_B);  // [buffer]: the MMAs reading it are complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
@@ -536,7 +459,9 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) k_heads_dw_tc(const float* __r
     // lanes 0..63: rows of delta_hi (quadrants hi*hi | hi*lo), lanes 64..127: rows of delta_lo (lo*hi | lo*lo)
     const int lane_row = warp * 32 + (tid & 31);
     const int j = lane_row & 63;
-    float* out = dW + ((size_t)head * L + layer) * U * U + (size_t)j * U;
+    // rows j (delta_hi) and 64 + j (delta_lo) of the accumulator both belong to output row j: the hi half goes to
+    // slot 0 of the partial tile pair, the lo half to slot 1; the reduce kernel adds them in that order
+    float* out = part_dW + ((((size_t)head * L + layer) * gridDim.x + blockIdx.x) * 2 + (lane_row >> 6)) * U * U + (size_t)j * U;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
     for (int c = 0; c < 64; c += 16) {
@@ -545,23 +470,34 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) k_heads_dw_tc(const float* __r
       tmem_ld16(taddr + 64 + c, y);
       tc_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) atomicAdd(out + c + i, __uint_as_float(x[i]) + __uint_as_float(y[i]));
+      for (int i = 0; i < 16; i += 4)
+        *reinterpret_cast<float4*>(out + c + i) =
+            make_float4(__uint_as_float(x[i]) + __uint_as_float(y[i]), __uint_as_float(x[i + 1]) + __uint_as_float(y[i + 1]),
+                        __uint_as_float(x[i + 2]) + __uint_as_float(y[i + 2]), __uint_as_float(x[i + 3]) + __uint_as_float(y[i + 3]));
     }
+  } else if (t == 0 && warp < 4) {  // a CTA without rows still owns its slots of the workspace
+    const int lane_row = warp * 32 + (tid & 31);
+    float* out = part_dW + ((((size_t)head * L + layer) * gridDim.x + blockIdx.x) * 2 + (lane_row >> 6)) * U * U + (size_t)(lane_row & 63) * U;
+    for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // bias gradient: reduce the per-thread column sums over the 32 rows of the warp, then one atomic per column
+  // bias gradient: reduce the per-thread column sums over the 32 rows of the warp; the two warps that share a column
+  // group (rows 0..31 and 32..63 of the tiles) are added in warp order
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    const int m8 = (tid + q * DWT_THREADS) >> 6;
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       float v = colsum[q][jj];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((tid & 31) == 0) atomicAdd(db + ((size_t)head * planes_per_head + layer) * U + m8 * 8 + jj, v);
+      if ((tid & 31) == 0) s_colsum[warp][q][jj] = v;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid < U) {  // column tid = 8 m8 + jj; unit u = tid' + 256 q has m8 = u >> 6: q = m8 >> 2, warps 2 (m8 & 3), 2 (m8 & 3) + 1
+    const int m8 = tid >> 3, jj = tid & 7, q = m8 >> 2, w0 = 2 * (m8 & 3);
+    part_db[(((size_t)head * L + layer) * gridDim.x + blockIdx.x) * U + tid] = s_colsum[w0][q][jj] + s_colsum[w0 + 1][q][jj];
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
 }
 
@@ -572,9 +508,8 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) k_heads_dw_tc(const float* __r
 // thread = (column chunk c4, row lane): 16 consecutive rows of one chunk per half warp (coalesced 256 B).
 __global__ void __launch_bounds__(256) k_heads_edge_grads(const float* __restrict__ act, const float* __restrict__ delta,
                                                           const float* __restrict__ x, const float* __restrict__ d_ll,
-                                                          float* __restrict__ g_in, float* __restrict__ db,
-                                                          float* __restrict__ g_out, long long P, int L, int sd,
-                                                          int rows_per_cta) {
+                                                          float* __restrict__ part_edge, long long P, int L, int sd,
+                                                          int rows_per_cta) {  // part_edge: [head][chunk][64][2 + MAX_SD]
   const int head = blockIdx.y;
   const size_t plane = ((size_t)head * (L + 1) + L) * (size_t)P * U;
   const float* A = act + plane;
@@ -615,61 +550,126 @@ __global__ void __launch_bounds__(256) k_heads_edge_grads(const float* __restric
     }
   }
   if (lane16 == 0) {
+    float* out = part_edge + ((size_t)head * gridDim.x + blockIdx.x) * U * (2 + MMF_MAX_SD);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int col = c4 * 4 + j;
-      atomicAdd(db + ((size_t)head * (L + 1) + L) * U + col, gb[j]);
-      atomicAdd(g_out + (size_t)head * U + col, go[j]);
+      float* o = out + (size_t)(c4 * 4 + j) * (2 + MMF_MAX_SD);
+      o[0] = gb[j];
+      o[1] = go[j];
 #pragma unroll
-      for (int d = 0; d < MMF_MAX_SD; ++d)
-        if (d < sd) atomicAdd(g_in + ((size_t)head * U + col) * sd + d, gi[j][d]);
+      for (int d = 0; d < MMF_MAX_SD; ++d) o[2 + d] = gi[j][d];
     }
   }
 }
 
+// second pass: adds the partials of every output element in chunk order (fixed => bit-reproducible)
+__global__ void k_heads_grads_reduce(const float* __restrict__ part_dW, const float* __restrict__ part_db,
+                                     const float* __restrict__ part_edge, int K, int L, int sd, int dw_chunks,
+                                     int edge_chunks, float* __restrict__ dW, float* __restrict__ db,
+                                     float* __restrict__ g_in, float* __restrict__ g_out) {
+  const long long n_dw = (long long)K * L * U * U, n_db = (long long)K * (L + 1) * U;
+  const long long n_in = (long long)K * U * sd, n_out = (long long)K * U;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_dw + n_db + n_in + n_out;
+       e += (long long)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    if (e < n_dw) {
+      const long long hl = e / (U * U), ij = e % (U * U);
+      const float* p = part_dW + (size_t)hl * dw_chunks * 2 * U * U + ij;
+      for (int c = 0; c < 2 * dw_chunks; ++c) s += p[(size_t)c * U * U];
+      dW[e] = s;
+    } else if (e < n_dw + n_db) {
+      const long long r = e - n_dw, head = r / ((L + 1) * U), layer = (r / U) % (L + 1), col = r % U;
+      if (layer < L) {
+        const float* p = part_db + ((size_t)(head * L + layer) * dw_chunks) * U + col;
+        for (int c = 0; c < dw_chunks; ++c) s += p[(size_t)c * U];
+      } else {
+        const float* p = part_edge + ((size_t)head * edge_chunks * U + col) * (2 + MMF_MAX_SD);
+        for (int c = 0; c < edge_chunks; ++c) s += p[(size_t)c * U * (2 + MMF_MAX_SD)];
+      }
+      db[r] = s;
+    } else if (e < n_dw + n_db + n_in) {
+      const long long r = e - n_dw - n_db, head = r / (U * sd), col = (r / sd) % U, d = r % sd;
+      const float* p = part_edge + ((size_t)head * edge_chunks * U + col) * (2 + MMF_MAX_SD) + 2 + d;
+      for (int c = 0; c < edge_chunks; ++c) s += p[(size_t)c * U * (2 + MMF_MAX_SD)];
+      g_in[r] = s;
+    } else {
+      const long long r = e - n_dw - n_db - n_in, head = r / U, col = r % U;
+      const float* p = part_edge + ((size_t)head * edge_chunks * U + col) * (2 + MMF_MAX_SD) + 1;
+      for (int c = 0; c < edge_chunks; ++c) s += p[(size_t)c * U * (2 + MMF_MAX_SD)];
+      g_out[r] = s;
+    }
+  }
+}
+
+// row partition of the weight-gradient kernels (a function of the device's SM count only)
+struct DwPartition {
+  long long dw_chunks, dw_rows, edge_chunks, edge_rows;
+};
+static DwPartition dw_partition(int K, int L, long long P, int sms) {
+  DwPartition q;
+  // tensor-core dW kernel: 3 CTAs of 64 KB fit an SM
+  q.dw_chunks = ((long long)sms * 3 + (long long)K * L - 1) / ((long long)K * L);
+  q.dw_rows = (P + q.dw_chunks - 1) / q.dw_chunks;
+  q.dw_rows = ((q.dw_rows + DWT_ROWS - 1) / DWT_ROWS) * DWT_ROWS;
+  q.dw_chunks = (P + q.dw_rows - 1) / q.dw_rows;
+  q.edge_chunks = ((long long)sms * 4 + K - 1) / K;
+  q.edge_rows = (P + q.edge_chunks - 1) / q.edge_chunks;
+  q.edge_rows = ((q.edge_rows + 15) / 16) * 16;
+  q.edge_chunks = (P + q.edge_rows - 1) / q.edge_rows;
+  return q;
+}
+static int current_sms(int* sms) {
+  int dev = 0;
+  *sms = 148;
+  MMF_CUDA(cudaGetDevice(&dev));
+  MMF_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return MMF_OK;
+}
+
+size_t heads_dw_workspace_bytes(int K, int L, long long P) {
+  int sms = 148;
+  if (P <= 0 || current_sms(&sms) != MMF_OK) return 0;
+  const DwPartition q = dw_partition(K, L, P, sms);
+  const size_t floats = (size_t)K * L * q.dw_chunks * (2 * U * U + U) + (size_t)K * q.edge_chunks * U * (2 + MMF_MAX_SD);
+  return floats * sizeof(float);
+}
+
 int launch_heads_dw(int K, int L, long long P, int sd, const float* act, const float* delta, const float* x,
-                    const float* d_ll, float* dW, float* db, float* g_in, float* g_out, cudaStream_t stream) {
+                    const float* d_ll, float* dW, float* db, float* g_in, float* g_out, void* workspace,
+                    cudaStream_t stream) {
   if (P == 0) return MMF_OK;
   int dev = 0, sms = 148;
   MMF_CUDA(cudaGetDevice(&dev));
-  MMF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // about 4 CTAs per SM in total, whole multiples of the staging depth per CTA
-  long long chunks = ((long long)sms * 4 + (long long)K * L - 1) / ((long long)K * L);
-  long long rows_per_cta = (P + chunks - 1) / chunks;
-  rows_per_cta = ((rows_per_cta + DW_ROWS - 1) / DW_ROWS) * DW_ROWS;
-  chunks = (P + rows_per_cta - 1) / rows_per_cta;
-  dim3 grid((unsigned)chunks, (unsigned)L, (unsigned)K);
-  int variant = 1;  // MMF_DW_VARIANT: 1 = tcgen05 (default), 0 = fp32 FFMA2 on the CUDA cores
-  if (const char* env = getenv("MMF_DW_VARIANT")) variant = atoi(env);
-  if (variant == 1) {
+  int rc = current_sms(&sms);
+  if (rc) return rc;
+  MMF_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0,
+              "heads_weight_grads: pass a 16-byte aligned workspace of mmf_pf_heads_weight_grads_workspace_bytes() bytes");
+  const DwPartition q = dw_partition(K, L, P, sms);
+  float* part_dW = static_cast<float*>(workspace);
+  float* part_db = part_dW + (size_t)K * L * q.dw_chunks * 2 * U * U;
+  float* part_edge = part_db + (size_t)K * L * q.dw_chunks * U;
+  {
     const size_t smem = 4 * DWT_OPERAND_B + 64;
     static thread_local int configured_dev = -1;
     static thread_local size_t window = 0;
     if (configured_dev != dev) {
-      int rc = opt_in_shared_memory(k_heads_dw_tc, &window);
+      rc = opt_in_shared_memory(k_heads_dw_tc, &window);
       if (rc) return rc;
       configured_dev = dev;
     }
     MMF_REQUIRE(smem <= window, "heads_weight_grads needs %zu B of shared memory (window %zu B)", smem, window);
-    // one CTA per SM-slot: 3 CTAs of 64 KB fit an SM
-    long long tc_chunks = ((long long)sms * 3 + (long long)K * L - 1) / ((long long)K * L);
-    long long tc_rows = (P + tc_chunks - 1) / tc_chunks;
-    tc_rows = ((tc_rows + DWT_ROWS - 1) / DWT_ROWS) * DWT_ROWS;
-    tc_chunks = (P + tc_rows - 1) / tc_rows;
-    k_heads_dw_tc<<<dim3((unsigned)tc_chunks, (unsigned)L, (unsigned)K), DWT_THREADS, smem, stream>>>(act, delta, dW, db, P,
-                                                                                                   L + 1, L, (int)tc_rows);
+    k_heads_dw_tc<<<dim3((unsigned)q.dw_chunks, (unsigned)L, (unsigned)K), DWT_THREADS, smem, stream>>>(
+        act, delta, part_dW, part_db, P, L + 1, L, (int)q.dw_rows);
     MMF_LAUNCH_CHECK("k_heads_dw_tc");
-  } else {
-    k_heads_dw<<<grid, DW_THREADS, 0, stream>>>(act, delta, dW, db, P, L + 1, L, (int)rows_per_cta);
-    MMF_LAUNCH_CHECK("k_heads_dw");
   }
-  long long edge_chunks = ((long long)sms * 4 + K - 1) / K;
-  long long edge_rows = (P + edge_chunks - 1) / edge_chunks;
-  edge_rows = ((edge_rows + 15) / 16) * 16;
-  edge_chunks = (P + edge_rows - 1) / edge_rows;
-  k_heads_edge_grads<<<dim3((unsigned)edge_chunks, (unsigned)K), 256, 0, stream>>>(act, delta, x, d_ll, g_in, db, g_out, P, L,
-                                                                                   sd, (int)edge_rows);
+  k_heads_edge_grads<<<dim3((unsigned)q.edge_chunks, (unsigned)K), 256, 0, stream>>>(act, delta, x, d_ll, part_edge, P, L, sd,
+                                                                                   (int)q.edge_rows);
   MMF_LAUNCH_CHECK("k_heads_edge_grads");
+  const long long outputs = (long long)K * L * U * U + (long long)K * (L + 1) * U + (long long)K * U * (sd + 1);
+  k_heads_grads_reduce<<<(unsigned)((outputs + 255) / 256), 256, 0, stream>>>(part_dW, part_db, part_edge, K, L, sd,
+                                                                            (int)q.dw_chunks, (int)q.edge_chunks, dW, db, g_in,
+                                                                            g_out);
+  MMF_LAUNCH_CHECK("k_heads_grads_reduce");
   return MMF_OK;
 }
 

@@ -25,7 +25,8 @@ struct PredictParams {
   long long total;
   const float* states_in;
   const float* eps;
-  const float* rowbias;  // (1+K, N, 64)
+  const float* rowbias;  // (1+K, rb_stride, 64)
+  int rb_stride;
   const float* logw_in;
   const float* modw;  // (N, K) or null
   float* states_out;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(TPB, 1) k_particle_chain_ffma(const __grid_con
         const bool first_half = !is_mid && ((rel & 1) == 0);
         const float* Wt = w;
         if (is_mid) {
-          const float4* rb = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
+          const float4* rb = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.rb_stride + n) * U);
 #pragma unroll
           for (int j4 = 0; j4 < U / 4; ++j4) {
             const float4 b = __ldg(rb + j4);
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(TPB, 1) k_particle_chain_ffma(const __grid_con
 int launch_particle_chain_ffma(const mmf_pf_model* model, int N, int M, const float* states_in,
                                const float* eps, const float* rowbias, const float* logw_in,
                                const float* modw, uint32_t enabled, float* states_out,
-                               float* logw_out, float* ll_out, cudaStream_t stream) {
+                               float* logw_out, float* ll_out, cudaStream_t stream, int rb_stride) {
   PredictParams P;
   P.K = model->num_heads;
   P.chains[0] = to_dev(model->dynamics);
@@ -228,6 +229,7 @@ int launch_particle_chain_ffma(const mmf_pf_model* model, int N, int M, const fl
   P.states_in = states_in;
   P.eps = eps;
   P.rowbias = rowbias;
+  P.rb_stride = rb_stride > 0 ? rb_stride : N;
   P.logw_in = logw_in;
   P.modw = modw;
   P.states_out = states_out;

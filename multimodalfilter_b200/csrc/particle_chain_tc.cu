@@ -24,6 +24,17 @@
 // Replaces the same reference lines as particle_chain_ffma.cu.
 #include "tc_common.cuh"
 
+#ifndef MMF_TC_ABLATE
+#define MMF_TC_ABLATE 0
+#endif
+#if MMF_TC_ABLATE == 3  // measurement build (tools/ubench): clock64 stamps of CTA 0's hand-overs, second tile of chain 0
+__device__ unsigned long long g_ws_stamps[2 * 16 * 4 * 4];
+#define MMF_STAMP(cond, role, layer, grp, k) \
+  do { if (cond) g_ws_stamps[(((role) * 16 + (layer)) * 4 + (grp)) * 4 + (k)] = clock64(); } while (0)
+#else
+#define MMF_STAMP(cond, role, layer, grp, k) do { } while (0)
+#endif
+
 namespace mmf {
 
 struct TcParams {
@@ -40,6 +51,7 @@ struct TcParams {
   const float* states_in;
   const float* eps;
   const float* rowbias;
+  int rb_stride;      // trajectories per rowbias plane (N, or T * N when the rows of a whole sequence were hoisted)
   const float* logw_in;
   const float* modw;
   float* states_out;
@@ -392,7 +404,7 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
 
         // ---- epilogue of this layer = producer of the next layer's A operand ---------------------------
         if (layer == mid_at) {
-          const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
+          const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.rb_stride + n) * U);
           float* arow = act_base ? act_base + (size_t)(layer + 1) * act_plane : nullptr;
           if (ch.mid_relu) epilogue<EPI_MID_RELU, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4);
           else epilogue<EPI_MID_LINEAR, TC_COLS>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4);
@@ -460,39 +472,71 @@ __global__ void __launch_bounds__(TC_GROUPS * 128, 1) k_particle_chain_tc(const 
 }
 
 
-// ---- warp-specialised kernel (the default, MMF_TC_VARIANT=71): ONE issuer warp feeds the tensor pipe -------------
-// In the symmetric kernel above every group issues its own MMAs.  The four issuing lanes block on the tensor
-// pipe's queue and their instructions interleave one by one in its FIFO, so the four accumulators complete at the
-// same moment and the SM alternates between "all groups in the epilogue" (issue-slot bound) and "all groups queued
-// at the tensor pipe": a layer costs epilogue time PLUS MMA time (ncu r01: tensor pipe 52 %, issue slots 59 %, and
-// 870 cycles per tile-layer = 450 issue + 384 tensor) instead of their maximum.  Here warp 4 G issues everything
-// and serves the groups round robin, one group's MMAs back to back: accumulators complete 384 cycles apart, the
-// groups' epilogues stay staggered, and the epilogue warps lose the issue code, the per-layer named barrier and
-// the divergent single-lane region from their instruction stream.
+// ---- warp-specialised kernel (the default): dedicated issuer warps feed the tensor pipe ---------------------------
+// In the symmetric kernel above every group issues its own MMAs from inside its epilogue warps.  Measured (ncu r01 and the
+// clock64 timeline of the measurement build, profiles/r02_*): a layer costs epilogue time PLUS MMA time instead of their
+// maximum.  Three facts from the timeline shape this kernel:
+//   * the tensor pipe's queue is one or two MMAs deep: the issuing lane blocks for ~32 cycles per MMA, so "issue 12 MMAs"
+//     takes as long as executing them (370-480 cycles) -> the issuing lane cannot do anything else;
+//   * waiting on an mbarrier that has ALREADY completed still costs ~130 cycles: one issuer serving the groups in turn
+//     leaves the pipe idle for that long between batches (600 cycles per tile-layer against 384 of tensor work);
+//   * tcgen05.commit -> waiting warps running again: ~190 cycles.
+// So: NI = 2 issuer warps (warps 4 G and 4 G + 1, issuer w serves groups w, w + NI, ...), each blocked on the pipe while
+// the other sits in its barrier wait; the pipe always has a batch to run, and at most NI accumulators complete together,
+// so the groups' epilogues stay staggered against the MMAs.  The epilogue warps lose the issue code, the per-layer named
+// barrier and the divergent single-lane region from their instruction stream, and hand over through mbarriers only:
 //   a_ready[g] (count 4): a warp of group g arrives once its part of the next A operand is in TMEM
-//   d_ready[g][h] (count 1): tcgen05.commit after the MMAs of (half h of) group g's accumulator
-// SPLIT = 2 issues a layer as two N = 32 batches, columns [0, 32) first: the group starts its epilogue on the
-// first half while the tensor pipe is still on the second.
-template <int KIND, int SPLIT>
+//   d_ready[g] (count 1): tcgen05.commit after the MMAs of group g's accumulator
+// At a tile boundary the next tile's input layer is computed and published BEFORE the finished tile's output arithmetic
+// (gate, noise, fusion, global loads and stores), whose latency would otherwise sit on the group's critical path.
+// mbarrier helpers on precomputed 32-bit shared-memory addresses (the generic-pointer wrappers re-derive the address,
+// cluster CTA id included, at every use: ~10 instructions per wait / arrive in the hot loop).  The wait parks the warp
+// in hardware for up to `hint` ns per attempt (it is woken by the completing arrive), so a waiting warp costs the
+// epilogue warps that share its scheduler almost no issue slots; the attempt bound turns a lost arrival into a trap.
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok, attempts = 0;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    if (!ok && ++attempts > (1u << 22)) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int KIND>
 __device__ __forceinline__ void epilogue_ws(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float4* __restrict__ bias4,
                                             float2 (&xr)[U / 2], bool single_pass, float* act_row, size_t act_stride4,
-                                            uint64_t* dbar, uint32_t (&dph)[2]) {
-  if (SPLIT == 1) {
-    mbar_wait(dbar, dph[0]);
-    dph[0] ^= 1;
-    tc_fence_after();
-    epilogue<KIND, U>(tD, tAhi, tAlo, bias4, xr, single_pass, act_row, act_stride4);
-  } else {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      mbar_wait(dbar + h, dph[h]);
-      dph[h] ^= 1;
-      tc_fence_after();
-      float2(&xh)[U / 4] = *reinterpret_cast<float2(*)[U / 4]>(&xr[h * (U / 4)]);
-      epilogue<KIND, U / 2>(tD + h * (U / 2), tAhi + h * (U / 4), tAlo + h * (U / 4), bias4 + h * (U / 8), xh, single_pass,
-                            act_row ? act_row + (size_t)(h * (U / 8)) * act_stride4 : nullptr, act_stride4);
-    }
-  }
+                                            uint32_t dbar, uint32_t& dph, uint32_t hint_ns,
+                                            unsigned long long* stamp = nullptr) {
+  mbar_wait_a(dbar, dph, hint_ns);
+  dph ^= 1;
+  tc_fence_after();
+#if MMF_TC_ABLATE == 3
+  if (stamp) *stamp = clock64();
+#endif
+#if MMF_TC_ABLATE != 2  // measurement build 2 (tools/ubench): no epilogue arithmetic -> MMA pipeline + hand-over alone
+  epilogue<KIND, U>(tD, tAhi, tAlo, bias4, xr, single_pass, act_row, act_stride4);
+#endif
+}
+
+// hand the A operand to the issuer: my TMEM stores have retired and are ordered before the arrive it observes
+__device__ __forceinline__ void ws_publish(uint32_t abar_g, bool lane0) {
+  tc_wait_st();
+  tc_fence_before();
+  __syncwarp();
+  if (lane0) mbar_arrive_a(abar_g);
 }
 
 // start of a chain phase, executed by ALL threads of the CTA: barrier, bulk copy of the chain's operand image into
@@ -514,29 +558,27 @@ __device__ __forceinline__ void ws_load_image(const TcParams& P, int c, uint8_t*
   wphase ^= 1;
 }
 
-template <int G, int SPLIT, bool TRAIN>
+template <int G, int NI, bool TRAIN>
 __global__ void __launch_bounds__(G * 128 + 128, 1) k_particle_chain_ws(const __grid_constant__ TcParams P) {
   constexpr int TC_CHUNKS = U / 16;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + P.image_cap);
-  uint64_t* dbar = wbar + 1;                      // [G][2]
-  uint64_t* abar = dbar + 2 * TC_MAX_GROUPS;      // [G]
+  uint64_t* dbar = wbar + 1;                  // [G]
+  uint64_t* abar = dbar + TC_MAX_GROUPS;      // [G]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(abar + TC_MAX_GROUPS);
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
-  const bool service = warp >= 4 * G;  // warps 4 G .. 4 G + 3: the issuer and three parked warps (a full warpgroup)
-  const bool issuer = warp == 4 * G;
-  const int g = warp >> 2;
-  const int row = tid & 127;  // particle row inside the tile == TMEM lane (workers)
+  const bool service = warp >= 4 * G;  // warps 4 G .. 4 G + 3: NI issuers and parked warps (a full warpgroup)
+  const int g = warp >> 2;             // worker: group
+  const int row = tid & 127;           // worker: particle row inside the tile == TMEM lane
   const int sd = P.sd;
   const bool single_pass = P.single_pass != 0;
 
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int i = 0; i < G; ++i) {
-      mbar_init(dbar + 2 * i, 1);
-      mbar_init(dbar + 2 * i + 1, 1);
+      mbar_init(dbar + i, 1);
       mbar_init(abar + i, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -550,15 +592,11 @@ __global__ void __launch_bounds__(G * 128 + 128, 1) k_particle_chain_ws(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;   // this warp's 32-lane quadrant
-  const uint32_t tD = tmem_base + (service ? 0 : g * 128) + lane_off;
-  const uint32_t tAhi = tD + 64, tAlo = tD + 96;
+  const uint32_t dbar_a = smem_u32(dbar), abar_a = smem_u32(abar);  // barrier i at + 8 i
+  const uint32_t hint_ns = P.wait_hint_ns;
   uint32_t wphase = 0;
-  uint32_t dph[2] = {0, 0};   // workers: parity of d_ready[g][h]
-  uint32_t aph = 0;           // issuer: bit i = parity of a_ready[i]
-
   const long long tiles = (P.total + 127) / 128;
-  constexpr uint32_t IDESC_L = make_idesc(U / SPLIT, 128);
+  constexpr uint32_t IDESC_L = make_idesc(U, 128);
   constexpr uint32_t IDESC_O = make_idesc(OUT_PAD, 128);
   const long long unit = blockIdx.x, units = gridDim.x;
 
@@ -567,67 +605,62 @@ __global__ void __launch_bounds__(G * 128 + 128, 1) k_particle_chain_ws(const __
     // 64 x 128 registers back to the CTA pool and the four worker warpgroups take 16 x 128 each: 112 registers for
     // the epilogue (fp32 residual stream 64 + two accumulator chunks in flight 32 + the split).
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    const int me = warp - 4 * G;  // issuer index (< NI) or parked
+    uint32_t aph = 0;             // bit i = parity of a_ready[i]
     for (int c = P.first_chain; c <= P.K; ++c) {
       if (c > 0 && !((P.enabled >> (c - 1)) & 1u)) continue;
-      const ChainDev ch = P.chains[c];
-      const int L = chain_layers(ch);
+      const int L = chain_layers(P.chains[c]);
       ws_load_image(P, c, smem, wbar, wphase);
-      if (!issuer) continue;
+      if (me >= NI) continue;
       const uint32_t tiles_addr = smem_u32(smem);
-      // ------------------------------------------------------------------------------------------ issuer warp
-        for (long long it = 0;; ++it) {
-          const long long tile0 = (it * units + unit) * G;
-          if (tile0 >= tiles) break;
-          const long long left = tiles - tile0;
-          const int ng = left < G ? (int)left : G;  // groups that have a tile in this slot
-          for (int layer = 0; layer <= L; ++layer) {
-            const bool is_out = layer == L;
-            const uint32_t hi_addr = tiles_addr + (is_out ? (uint32_t)L * 2 * TILE_B : (uint32_t)layer * 2 * TILE_B);
-            const uint32_t lo_addr = hi_addr + (is_out ? OUT_TILE_B : TILE_B);
-            const uint64_t bhi = make_b_desc(hi_addr), blo = make_b_desc(lo_addr);
+      for (long long it = 0;; ++it) {
+        const long long tile0 = (it * units + unit) * G;
+        if (tile0 >= tiles) break;
+        const long long left = tiles - tile0;
+        const int ng = left < G ? (int)left : G;  // groups that have a tile in this slot
+        for (int layer = 0; layer <= L; ++layer) {
+          const bool is_out = layer == L;
+          const uint32_t hi_addr = tiles_addr + (is_out ? (uint32_t)L * 2 * TILE_B : (uint32_t)layer * 2 * TILE_B);
+          const uint32_t lo_addr = hi_addr + (is_out ? OUT_TILE_B : TILE_B);
+          const uint64_t bhi = make_b_desc(hi_addr), blo = make_b_desc(lo_addr);
+          const uint32_t idesc = is_out ? IDESC_O : IDESC_L;
 #pragma unroll
-            for (int i = 0; i < G; ++i) {
-              if (i >= ng) break;
-              mbar_wait(abar + i, (aph >> i) & 1u);
-              aph ^= 1u << i;
-              tc_fence_after();
-              if (elect_one_sync()) {
-                const uint32_t d = tmem_base + i * 128, a_hi = d + 64, a_lo = d + 96;
-                if (is_out) {
+          for (int k0 = 0; k0 < G; k0 += NI) {
+            const int i = k0 + me;
+            if (i >= ng) break;
+            MMF_STAMP(blockIdx.x == 0 && c == 0 && it == 1 && (tid & 31) == 0, 0, layer, i, 0);
+            mbar_wait_a(abar_a + 8 * i, (aph >> i) & 1u, hint_ns);
+            aph ^= 1u << i;
+            tc_fence_after();
+            MMF_STAMP(blockIdx.x == 0 && c == 0 && it == 1 && (tid & 31) == 0, 0, layer, i, 1);
+            if (elect_one_sync()) {
+              const uint32_t d = tmem_base + i * 128, a_hi = d + 64, a_lo = d + 96;
+#if MMF_TC_ABLATE != 1  // measurement build 1 (tools/ubench): no MMAs, the commit arrives at once -> epilogue pipeline alone
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + k * 8, bhi + (uint64_t)(k * 2), IDESC_O, k > 0);
-                  if (!single_pass) {
+              for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + k * 8, bhi + (uint64_t)(k * 2), idesc, k > 0);
+              if (!single_pass) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + k * 8, blo + (uint64_t)(k * 2), IDESC_O, 1);
+                for (int k = 0; k < 4; ++k) mma_ts(d, a_hi + k * 8, blo + (uint64_t)(k * 2), idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) mma_ts(d, a_lo + k * 8, bhi + (uint64_t)(k * 2), IDESC_O, 1);
-                  }
-                  tc_commit(dbar + 2 * i);
-                } else {
-#pragma unroll
-                  for (int h = 0; h < SPLIT; ++h) {
-                    // half h: accumulator columns [32 h, 32 h + 32) = weight rows [32 h, +32) = 4096 h bytes into the tile
-                    const uint64_t bh = bhi + (uint64_t)(h * (4096 >> 4)), bl = blo + (uint64_t)(h * (4096 >> 4));
-                    const uint32_t dh = d + h * (U / 2);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) mma_ts(dh, a_hi + k * 8, bh + (uint64_t)(k * 2), IDESC_L, k > 0);
-                    if (!single_pass) {
-#pragma unroll
-                      for (int k = 0; k < 4; ++k) mma_ts(dh, a_hi + k * 8, bl + (uint64_t)(k * 2), IDESC_L, 1);
-#pragma unroll
-                      for (int k = 0; k < 4; ++k) mma_ts(dh, a_lo + k * 8, bh + (uint64_t)(k * 2), IDESC_L, 1);
-                    }
-                    tc_commit(dbar + 2 * i + h);
-                  }
-                }
+                for (int k = 0; k < 4; ++k) mma_ts(d, a_lo + k * 8, bhi + (uint64_t)(k * 2), idesc, 1);
               }
-              __syncwarp();
+#endif
+              tc_commit_a(dbar_a + 8 * i);
             }
+            __syncwarp();
+            MMF_STAMP(blockIdx.x == 0 && c == 0 && it == 1 && (tid & 31) == 0, 0, layer, i, 2);
           }
         }
+      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // this warp's 32-lane quadrant
+    const uint32_t tD = tmem_base + g * 128 + lane_off;
+    const uint32_t tAhi = tD + 64, tAlo = tD + 96;
+    uint32_t dph = 0;  // parity of d_ready[g]
+    const uint32_t my_dbar = dbar_a + 8 * g, my_abar = abar_a + 8 * g;
+    const bool lane0 = (tid & 31) == 0;
     for (int c = P.first_chain; c <= P.K; ++c) {
       if (c > 0 && !((P.enabled >> (c - 1)) & 1u)) continue;
       const ChainDev ch = P.chains[c];
@@ -639,97 +672,123 @@ __global__ void __launch_bounds__(G * 128 + 128, 1) k_particle_chain_ws(const __
       }
       ws_load_image(P, c, smem, wbar, wphase);
 
-      // --------------------------------------------------------------------------------------------- worker groups
       const float* fsm = reinterpret_cast<const float*>(smem + image_tiles_bytes(ch, 1));
       const float* in_Wt = fsm;
       const float* in_b = fsm + ch.in_dim * U;
       const float* biases = in_b + U;
       const float* out_b = biases + L * U;
       const int mid_at = 2 * ch.n_pre;
-      uint64_t* my_dbar = dbar + 2 * g;
+      const float* xsrc = (c == 0) ? P.states_in : P.states_out;
+      const size_t act_plane = (size_t)P.total * U;
+      const size_t act_stride4 = (size_t)P.total * 4;
+      const long long tile_step = units * G;
 
-      for (long long it = 0;; ++it) {
-        const long long tile = (it * units + unit) * G + g;
-        if (tile >= tiles) break;
-        const long long p_raw = tile * 128 + row;
-        const bool live = p_raw < P.total;
-        const long long p = live ? p_raw : P.total - 1;
-        const int n = (int)(p / P.M);
-        const float* xsrc = (c == 0) ? P.states_in : P.states_out;
-        float x[MMF_MAX_SD];
+      float2 xr[U / 2];  // fp32 residual stream of this thread's row
+      // input layer on the CUDA cores: xr = relu(in_W x + in_b) -> A operand (and, training, activation plane 0)
+      auto input_layer = [&](const float (&x)[MMF_MAX_SD], float* act_base) {
+        const float4* b4 = reinterpret_cast<const float4*>(in_b);
+        const float4* w4 = reinterpret_cast<const float4*>(in_Wt);
 #pragma unroll
-        for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
-
-        // training: base of this particle's saved activations for head c (layer index selects the plane)
-        float* act_base = (TRAIN && P.act_out != nullptr && c > 0 && live)
-                              ? P.act_out + (size_t)(c - 1) * (L + 1) * P.total * U + (size_t)p * 4
-                              : nullptr;
-        const size_t act_plane = (size_t)P.total * U;
-        const size_t act_stride4 = (size_t)P.total * 4;
-
-        // ---- input layer on the CUDA cores: xr = relu(in_W x + in_b) -> A operand ------------------------
-        float2 xr[U / 2];
-        {
-          const float4* b4 = reinterpret_cast<const float4*>(in_b);
-          const float4* w4 = reinterpret_cast<const float4*>(in_Wt);
+        for (int chunk = 0; chunk < TC_CHUNKS; ++chunk) {
+          float2 v[8];
 #pragma unroll
-          for (int chunk = 0; chunk < TC_CHUNKS; ++chunk) {
-            float2 v[8];
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 t = b4[chunk * 4 + q4];
+            v[2 * q4] = make_float2(t.x, t.y);
+            v[2 * q4 + 1] = make_float2(t.z, t.w);
+          }
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const float4 t = b4[chunk * 4 + q4];
-              v[2 * q4] = make_float2(t.x, t.y);
-              v[2 * q4 + 1] = make_float2(t.z, t.w);
-            }
+          for (int i = 0; i < MMF_MAX_SD; ++i) {
+            if (i < sd) {
+              const float2 xi = make_float2(x[i], x[i]);
 #pragma unroll
-            for (int i = 0; i < MMF_MAX_SD; ++i) {
-              if (i < sd) {
-                const float2 xi = make_float2(x[i], x[i]);
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  const float4 t = w4[i * (U / 4) + chunk * 4 + q4];
-                  v[2 * q4] = __ffma2_rn(make_float2(t.x, t.y), xi, v[2 * q4]);
-                  v[2 * q4 + 1] = __ffma2_rn(make_float2(t.z, t.w), xi, v[2 * q4 + 1]);
-                }
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 t = w4[i * (U / 4) + chunk * 4 + q4];
+                v[2 * q4] = __ffma2_rn(make_float2(t.x, t.y), xi, v[2 * q4]);
+                v[2 * q4 + 1] = __ffma2_rn(make_float2(t.z, t.w), xi, v[2 * q4 + 1]);
               }
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[j].x = fmaxf(v[j].x, 0.0f);
-              v[j].y = fmaxf(v[j].y, 0.0f);
-              xr[chunk * 8 + j] = v[j];
-            }
-            if (TRAIN && act_base != nullptr) store_act_chunk(act_base, chunk, v, act_stride4);
-            store_a_chunk<false>(v, tAhi, tAlo, chunk, single_pass);
           }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j].x = fmaxf(v[j].x, 0.0f);
+            v[j].y = fmaxf(v[j].y, 0.0f);
+            xr[chunk * 8 + j] = v[j];
+          }
+          if (TRAIN && act_base != nullptr) store_act_chunk(act_base, chunk, v, act_stride4);
+          store_a_chunk<false>(v, tAhi, tAlo, chunk, single_pass);
         }
+      };
+      // training: base of a particle's saved activations for head c (the layer index selects the plane)
+      auto act_of = [&](long long p, bool live) -> float* {
+        return (TRAIN && P.act_out != nullptr && c > 0 && live)
+                   ? P.act_out + (size_t)(c - 1) * (L + 1) * P.total * U + (size_t)p * 4
+                   : nullptr;
+      };
 
-        // ---- 64x64 layers ----------------------------------------------------------------------------------
+      long long tile = unit * G + g;
+      if (tile >= tiles) continue;
+      long long p_raw = tile * 128 + row;
+      bool live = p_raw < P.total;
+      long long p = live ? p_raw : P.total - 1;
+      float x[MMF_MAX_SD];
+#pragma unroll
+      for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = (i < sd) ? xsrc[p * sd + i] : 0.0f;
+      float* act_base = act_of(p, live);
+      input_layer(x, act_base);
+      ws_publish(my_abar, lane0);
+
+      for (long long it = 0;; ++it) {
+        const int n = (int)(p / P.M);
+        {  // the mid layer reads this trajectory's hoisted row from global memory right after its barrier wait: have
+           // it in L1 by then (two 128-byte lines; the 128 rows of a tile share a handful of trajectories)
+          const float* brow = P.rowbias + ((size_t)c * P.rb_stride + n) * U;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(brow));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(brow + 32));
+        }
+        // ---- 64x64 layers: wait for the accumulator, epilogue = next A operand, hand it over -------------------------
         for (int layer = 0; layer < L; ++layer) {
-          // hand the A operand to the issuer: my stores have retired and are ordered before the arrive it observes
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(abar + g);
+          MMF_STAMP(blockIdx.x == 0 && c == 0 && it == 1 && (tid & 127) == 0, 1, layer, g, 0);
           float* arow = (TRAIN && act_base) ? act_base + (size_t)(layer + 1) * act_plane : nullptr;
+#if MMF_TC_ABLATE == 3
+          unsigned long long* st = (blockIdx.x == 0 && c == 0 && it == 1 && (tid & 127) == 0) ? &g_ws_stamps[((16 + layer) * 4 + g) * 4 + 1] : nullptr;
+#else
+          unsigned long long* st = nullptr;
+#endif
           if (layer == mid_at) {
-            const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.N + n) * U);
-            if (ch.mid_relu) epilogue_ws<EPI_MID_RELU, SPLIT>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4, my_dbar, dph);
-            else epilogue_ws<EPI_MID_LINEAR, SPLIT>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4, my_dbar, dph);
+            const float4* brow = reinterpret_cast<const float4*>(P.rowbias + ((size_t)c * P.rb_stride + n) * U);
+            if (ch.mid_relu) epilogue_ws<EPI_MID_RELU>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4, my_dbar, dph, hint_ns, st);
+            else epilogue_ws<EPI_MID_LINEAR>(tD, tAhi, tAlo, brow, xr, single_pass, arow, act_stride4, my_dbar, dph, hint_ns, st);
           } else {
             const int rel = (layer < mid_at) ? layer : layer - mid_at - 1;
             const float4* bsm = reinterpret_cast<const float4*>(biases + layer * U);
-            if ((rel & 1) == 0) epilogue_ws<EPI_RES_A, SPLIT>(tD, tAhi, tAlo, bsm, xr, single_pass, arow, act_stride4, my_dbar, dph);
-            else epilogue_ws<EPI_RES_B, SPLIT>(tD, tAhi, tAlo, bsm, xr, single_pass, arow, act_stride4, my_dbar, dph);
+            if ((rel & 1) == 0) epilogue_ws<EPI_RES_A>(tD, tAhi, tAlo, bsm, xr, single_pass, arow, act_stride4, my_dbar, dph, hint_ns, st);
+            else epilogue_ws<EPI_RES_B>(tD, tAhi, tAlo, bsm, xr, single_pass, arow, act_stride4, my_dbar, dph, hint_ns, st);
           }
+          MMF_STAMP(blockIdx.x == 0 && c == 0 && it == 1 && (tid & 127) == 0, 1, layer, g, 2);
+          ws_publish(my_abar, lane0);  // after the last layer: the A operand of the output layer
         }
-        // ---- output layer -------------------------------------------------------------------------------------
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(abar + g);
-        mbar_wait(my_dbar, dph[0]);
-        dph[0] ^= 1;
+        // ---- tile boundary: fetch the next tile's particle while the output layer is in the tensor pipe -------------
+        const long long tile_n = tile + tile_step;
+        const bool have_next = tile_n < tiles;
+        const long long pn_raw = tile_n * 128 + row;
+        const bool live_n = have_next && pn_raw < P.total;
+        const long long p_n = live_n ? pn_raw : P.total - 1;
+        float xn[MMF_MAX_SD];
+#pragma unroll
+        for (int i = 0; i < MMF_MAX_SD; ++i) xn[i] = (have_next && i < sd) ? xsrc[p_n * sd + i] : 0.0f;
+        // operands of the output arithmetic, fetched early as well
+        float e[MMF_MAX_SD], prev = 0.0f, lw_in = 0.0f, mw = 0.0f;
+        if (c == 0) {
+#pragma unroll
+          for (int i = 0; i < MMF_MAX_SD; ++i) e[i] = (i < sd) ? P.eps[p * sd + i] : 0.0f;
+        } else {
+          if (!first_head) prev = P.logw_out[p];
+          if (last_head) lw_in = P.logw_in[p];
+          if (P.modw != nullptr) mw = __ldg(P.modw + (size_t)n * P.K + (c - 1));
+        }
+        mbar_wait_a(my_dbar, dph, hint_ns);
+        dph ^= 1;
         tc_fence_after();
         float y[MMF_MAX_SD + 1];
         {
@@ -739,16 +798,20 @@ __global__ void __launch_bounds__(G * 128 + 128, 1) k_particle_chain_ws(const __
 #pragma unroll
           for (int o = 0; o < MMF_MAX_SD + 1; ++o) y[o] = __uint_as_float(d[o]) + out_b[o];
         }
-
+        // the output-layer MMA has completed: its A operand and accumulator are free -> next tile's input layer first
+        float* act_base_n = nullptr;
+        if (have_next) {
+          act_base_n = act_of(p_n, live_n);
+          input_layer(xn, act_base_n);
+          ws_publish(my_abar, lane0);
+        }
+        // ---- output arithmetic of the finished tile -----------------------------------------------------------------
         if (c == 0) {
           float gsel = 0.0f;
 #pragma unroll
           for (int o = 0; o < MMF_MAX_SD + 1; ++o)
             if (o == sd) gsel = y[o];
           const float gate = 1.0f / (1.0f + expf(-gsel));
-          float e[MMF_MAX_SD];
-#pragma unroll
-          for (int i = 0; i < MMF_MAX_SD; ++i) e[i] = (i < sd) ? P.eps[p * sd + i] : 0.0f;
 #pragma unroll
           for (int i = 0; i < MMF_MAX_SD; ++i) {
             if (i < sd) {
@@ -763,19 +826,23 @@ __global__ void __launch_bounds__(G * 128 + 128, 1) k_particle_chain_ws(const __
         } else {
           const float ll = y[0];
           if (P.ll_out != nullptr && live) P.ll_out[(size_t)(c - 1) * P.total + p] = ll;
-          const float v = ll + (P.modw != nullptr ? __ldg(P.modw + (size_t)n * P.K + (c - 1)) : 0.0f);
+          const float v = ll + mw;
           float fused = v;
           if (!first_head) {  // running log-sum-exp kept in logw_out between head phases
-            const float prev = P.logw_out[p];
             const float mx = fmaxf(prev, v);
             fused = (mx == -INFINITY) ? -INFINITY : mx + logf(expf(prev - mx) + expf(v - mx));
           }
-          if (live) P.logw_out[p] = last_head ? P.logw_in[p] + fused : fused;
+          if (live) P.logw_out[p] = last_head ? lw_in + fused : fused;
         }
-        // the next tile's input layer overwrites the A region: the out-layer MMA that read it has completed
+        if (!have_next) break;
+        tile = tile_n;
+        p = p_n;
+        live = live_n;
+        act_base = act_base_n;
+#pragma unroll
+        for (int i = 0; i < MMF_MAX_SD; ++i) x[i] = xn[i];
       }
     }
-
   }
 
   tc_fence_before();
@@ -784,20 +851,29 @@ __global__ void __launch_bounds__(G * 128 + 128, 1) k_particle_chain_ws(const __
 }
 
 // Pipeline shape, fixed when the library is loaded (environment MMF_TC_VARIANT, read once: no getenv on the launch
-// path): 71 = warp-specialised, one issuer warp + 4 groups (default); 72 = same, layers issued as two N = 32 halves;
-// 73 = 3 groups; 41 / 31 = symmetric kernel, every group issues its own MMAs; 42 / 32 = symmetric, CTA pairs.
+// path): 72 = warp-specialised, 4 groups + 2 issuer warps (default); 71 / 74 = same with 1 / 4 issuer warps;
+// 41 / 31 = symmetric kernel, every group issues its own MMAs; 42 / 32 = symmetric, CTA pairs.
 static int tc_variant() {
   static const int variant = [] {
     const char* env = getenv("MMF_TC_VARIANT");
-    return env ? atoi(env) : 71;
+    return env ? atoi(env) : 72;
   }();
   return variant;
+}
+
+// Hardware park time per mbarrier wait attempt in the warp-specialised kernel (ns; MMF_TC_WAIT_HINT, read once).
+static uint32_t tc_wait_hint() {
+  static const uint32_t hint = [] {
+    const char* env = getenv("MMF_TC_WAIT_HINT");
+    return env ? (uint32_t)atoi(env) : 20000u;
+  }();
+  return hint;
 }
 
 int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const float* states_in, const float* eps,
                              const float* rowbias, const float* logw_in, const float* modw, uint32_t enabled,
                              int precision, float* states_out, float* logw_out, float* ll_out, cudaStream_t stream,
-                             int first_chain, float* act_out) {
+                             int first_chain, float* act_out, int rb_stride) {
   const int variant = tc_variant();
   const bool pair = variant < 70 && (variant % 10) == 2;
   TcParams P;
@@ -824,13 +900,14 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
   P.states_in = states_in;
   P.eps = eps;
   P.rowbias = rowbias;
+  P.rb_stride = rb_stride > 0 ? rb_stride : N;
   P.logw_in = logw_in;
   P.modw = modw;
   P.states_out = states_out;
   P.logw_out = logw_out;
   P.ll_out = ll_out;
   for (int i = 0; i < MMF_MAX_SD * MMF_MAX_SD; ++i) P.q[i] = model->q_tril[i];
-  P.wait_hint_ns = 0;
+  P.wait_hint_ns = tc_wait_hint();
   P.first_chain = first_chain;
   P.act_out = act_out;
 
@@ -867,14 +944,14 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
     cfg.numAttrs = 1;                                                                             \
     MMF_CUDA(cudaLaunchKernelEx(&cfg, k_particle_chain_tc<G, PAIRED>, P));                        \
   } while (0)
-#define MMF_WS_LAUNCH(G, SPLIT)                                                                    \
+#define MMF_WS_LAUNCH(G, NI)                                                                       \
   do {                                                                                            \
     static thread_local int configured_dev = -1;                                                  \
     static thread_local size_t window = 0;                                                        \
     if (configured_dev != dev) {                                                                  \
-      int rc = opt_in_shared_memory(k_particle_chain_ws<G, SPLIT, false>, &window);               \
+      int rc = opt_in_shared_memory(k_particle_chain_ws<G, NI, false>, &window);               \
       if (rc) return rc;                                                                          \
-      rc = opt_in_shared_memory(k_particle_chain_ws<G, SPLIT, true>, &window);                    \
+      rc = opt_in_shared_memory(k_particle_chain_ws<G, NI, true>, &window);                    \
       if (rc) return rc;                                                                          \
       configured_dev = dev;                                                                       \
     }                                                                                             \
@@ -882,15 +959,15 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
     long long units = (tiles + G - 1) / G;                                                        \
     if (units > sms) units = sms;                                                                 \
     if (act_out != nullptr)                                                                       \
-      k_particle_chain_ws<G, SPLIT, true><<<(unsigned)units, G * 128 + 128, smem, stream>>>(P);   \
+      k_particle_chain_ws<G, NI, true><<<(unsigned)units, G * 128 + 128, smem, stream>>>(P);   \
     else                                                                                          \
-      k_particle_chain_ws<G, SPLIT, false><<<(unsigned)units, G * 128 + 128, smem, stream>>>(P);  \
+      k_particle_chain_ws<G, NI, false><<<(unsigned)units, G * 128 + 128, smem, stream>>>(P);  \
     MMF_LAUNCH_CHECK("k_particle_chain_ws");                                                      \
     return MMF_OK;                                                                                \
   } while (0)
-  if (variant == 71) MMF_WS_LAUNCH(4, 1);
   if (variant == 72) MMF_WS_LAUNCH(4, 2);
-  if (variant == 73) MMF_WS_LAUNCH(3, 1);
+  if (variant == 71) MMF_WS_LAUNCH(4, 1);
+  if (variant == 74) MMF_WS_LAUNCH(4, 4);
 #undef MMF_WS_LAUNCH
   switch (variant) {
     case 41: MMF_TC_LAUNCH(4, false); break;
@@ -905,3 +982,10 @@ int launch_particle_chain_tc(const mmf_pf_model* model, int N, int M, const floa
 }
 
 }  // namespace mmf
+
+#if MMF_TC_ABLATE == 3
+extern "C" int mmf_debug_ws_stamps(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, ::g_ws_stamps, sizeof(unsigned long long) * 2 * 16 * 4 * 4);
+}
+#endif

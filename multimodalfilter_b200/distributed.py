@@ -4,7 +4,8 @@ The forward / eval recursion needs NO collective (every reduction is inside one 
 SURVEY.md section 8e); the only exchange on the path is the gradient all-reduce of BPTT training
 (NCCL over NVLink on the GPU box, gloo in the CPU tests).
 """
-from typing import Dict, Tuple
+import ctypes as C
+from typing import Dict, Iterable, Tuple
 
 import torch
 import torch.distributed as dist
@@ -61,6 +62,89 @@ def allreduce_gradients(module: torch.nn.Module, average: bool = True) -> int:
         g.copy_(flat[offset:offset + n].view_as(g))
         offset += n
     return flat.numel()
+
+
+class FlatGradients:
+    """All parameter gradients of a training step as views into ONE flat fp32 buffer (the layout DDP calls
+    ``gradient_as_bucket_view``): autograd accumulates into the views in place, the collective and the optimiser read the
+    same memory, and there is no concatenate / copy-back around the all-reduce.  Call ``zero()`` instead of
+    ``optimizer.zero_grad(set_to_none=True)`` (which would detach the views)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
+        offset = 0
+        for p in self.params:
+            assert p.dtype == torch.float32 and p.device == dev
+            p.grad = self.flat[offset:offset + p.numel()].view_as(p)
+            offset += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def intact(self) -> bool:
+        """True while every ``p.grad`` still is the view handed out at construction."""
+        base = self.flat.data_ptr()
+        end = base + self.flat.numel() * 4
+        return all(p.grad is not None and base <= p.grad.data_ptr() < end for p in self.params)
+
+
+class _NcclUniqueId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
+class StreamAllReduce:
+    """The BPTT step's only collective, issued as ``ncclAllReduce`` DIRECTLY on the caller's CUDA stream (ctypes on the
+    NCCL library torch has already loaded; its own communicator, bootstrapped once through ``torch.distributed``).  On the
+    stream it is a plain stream-ordered kernel launch: it can be captured into the CUDA graph of the training step together
+    with forward, backward and the optimiser, which torch's process-group wrapper (side stream, watchdog, work objects)
+    could not (round 1: the capture hung).  NVLink / NVSwitch transport, in-switch reduction when NCCL selects NVLS.
+    Single process / no process group: a no-op."""
+
+    FLOAT32, SUM, AVG = 7, 0, 4
+
+    def __init__(self, device: torch.device):
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.device = device
+        self.comm = None
+        if self.world == 1:
+            return
+        assert device.type == "cuda", "StreamAllReduce is the NCCL path; CPU tests use allreduce_gradients (gloo)"
+        self.lib = C.CDLL("libnccl.so.2")
+        self.lib.ncclGetErrorString.restype = C.c_char_p
+        uid = _NcclUniqueId()
+        if dist.get_rank() == 0:
+            self._check(self.lib.ncclGetUniqueId(C.byref(uid)))
+        box = [bytes(uid.internal)] if dist.get_rank() == 0 else [None]
+        dist.broadcast_object_list(box, src=0, device=device)
+        C.memmove(C.byref(uid), box[0], 128)
+        comm = C.c_void_p()
+        with torch.cuda.device(device):
+            self._check(self.lib.ncclCommInitRank(C.byref(comm), C.c_int(self.world), uid, C.c_int(dist.get_rank())))
+        self.comm = comm
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"NCCL error {rc}: {self.lib.ncclGetErrorString(C.c_int(rc)).decode()}")
+
+    def __call__(self, flat: torch.Tensor, average: bool = True) -> int:
+        """In-place all-reduce of a contiguous fp32 tensor on the current stream of its device."""
+        if self.comm is None:
+            return 0
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()
+        stream = torch.cuda.current_stream(flat.device).cuda_stream
+        with torch.cuda.device(flat.device):
+            self._check(self.lib.ncclAllReduce(C.c_void_p(flat.data_ptr()), C.c_void_p(flat.data_ptr()),
+                                               C.c_size_t(flat.numel()), C.c_int(self.FLOAT32),
+                                               C.c_int(self.AVG if average else self.SUM), self.comm, C.c_void_p(stream)))
+        return flat.numel()
+
+    def close(self):
+        if self.comm is not None:
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = None
 
 
 def max_over_ranks(value: float, device) -> float:

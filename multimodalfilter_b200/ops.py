@@ -149,20 +149,24 @@ def rows_view(t):
 def pf_heads_weight_grads(act, delta, states, d_ll):
     """act, delta (K, L+1, 16, P, 4), states (P, sd), d_ll (K, P) -> parameter gradients of every head:
     dW (K, L, 64, 64) = delta_l^T a_l, db (K, L+1, 64) = column sums of delta (plane L: the input layer),
-    g_in (K, 64, sd) = delta_L^T states, g_out (K, 64) = a_L^T d_ll."""
+    g_in (K, 64, sd) = delta_L^T states, g_out (K, 64) = a_L^T d_ll.  Deterministic: per-CTA partial sums go through a
+    workspace and are added in a fixed order (three launches: dW, the two thin end layers, the reduction)."""
     lib = _lib.load()
     K, Lp1, _, P, _ = act.shape
     sd = states.shape[1]
     dev, U = act.device, _lib.UNITS
-    dW = torch.zeros((K, Lp1 - 1, U, U), device=dev, dtype=torch.float32)
-    db = torch.zeros((K, Lp1, U), device=dev, dtype=torch.float32)
-    g_in = torch.zeros((K, U, sd), device=dev, dtype=torch.float32)
-    g_out = torch.zeros((K, U), device=dev, dtype=torch.float32)
+    dW = torch.empty((K, Lp1 - 1, U, U), device=dev, dtype=torch.float32)
+    db = torch.empty((K, Lp1, U), device=dev, dtype=torch.float32)
+    g_in = torch.empty((K, U, sd), device=dev, dtype=torch.float32)
+    g_out = torch.empty((K, U), device=dev, dtype=torch.float32)
     states, d_ll = _f32c(states), _f32c(d_ll)
+    with torch.cuda.device(dev):
+        need = lib.mmf_pf_heads_weight_grads_workspace_bytes(K, Lp1 - 1, P)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)  # stream-ordered, graph-capture safe
     _lib.check(
-        PROFILE.run("pf_heads_weight_grads", 2, lib.mmf_pf_heads_weight_grads, K, Lp1 - 1, P, sd, _lib.ptr(act),
+        PROFILE.run("pf_heads_weight_grads", 3, lib.mmf_pf_heads_weight_grads, K, Lp1 - 1, P, sd, _lib.ptr(act),
                     _lib.ptr(delta), _lib.ptr(states), _lib.ptr(d_ll), _lib.ptr(dW), _lib.ptr(db), _lib.ptr(g_in),
-                    _lib.ptr(g_out), _lib.stream_of(act))
+                    _lib.ptr(g_out), _lib.ptr(ws), _lib.stream_of(act))
     )
     return dW, db, g_in, g_out
 
@@ -320,6 +324,48 @@ def pf_predict_measure(model_struct, states, eps, rowbias, logw, modality_logw, 
         )
     )
     return (states_out, logw_out, ll) if want_ll else (states_out, logw_out)
+
+
+def pf_forward_loop(model_struct, states, logw, controls, feats, modality_logw, enabled_mask, eps, *, precision,
+                    estimation, mode, uniforms):
+    """R1: the whole T-step recursion in one C call (1 + 2 T kernel launches).  states (N,M,sd) and logw (N,M) are
+    UPDATED IN PLACE to the particle set after the last step; controls (T,N,cd), feats: K tensors (T,N,F_k) or None,
+    modality_logw (T,N,K)|None, eps (T,N*M,sd), uniforms float64 (T,N,M) | (T,N) | None.  Returns estimates (T,N,sd)."""
+    lib = _lib.load()
+    N, M, sd = states.shape
+    T = controls.shape[0]
+    K = model_struct.num_heads
+    assert states.dtype == torch.float32 and states.is_contiguous() and logw.is_contiguous() and logw.shape == (N, M)
+    controls, eps = _f32c(controls), _f32c(eps)
+    assert controls.shape[:2] == (T, N) and eps.numel() == T * N * M * sd
+    feats = [None if f is None else _f32c(f) for f in feats]
+    assert len(feats) == K and all(f is None or f.shape[:2] == (T, N) for f in feats), "observation features / (T, N) mismatch"
+    arr = (C.c_void_p * _lib.MAX_HEADS)()
+    for k in range(K):
+        arr[k] = None if feats[k] is None else feats[k].data_ptr()
+    if modality_logw is not None:
+        modality_logw = _f32c(modality_logw)
+        assert modality_logw.shape == (T, N, K), (modality_logw.shape, (T, N, K))
+    dev = states.device
+    if mode != RESAMPLE_NONE:
+        assert uniforms is not None and uniforms.dtype == torch.float64
+        uniforms = uniforms.contiguous()
+        assert uniforms.shape == ((T, N) if is_systematic(mode) else (T, N, M)), uniforms.shape
+    rowbias = torch.empty((1 + K, T * N, _lib.UNITS), device=dev, dtype=torch.float32)
+    states_ws, logw_ws = torch.empty_like(states), torch.empty_like(logw)
+    est = torch.empty((T, N, sd), device=dev, dtype=torch.float32)
+    ws = _resample_workspace(N, M, dev)
+    for f in feats:  # note the feature tensors' device for the launch guard (their pointers travel in `arr`)
+        _lib.ptr(f)
+    _lib.check(
+        PROFILE.run(
+            "pf_forward_loop", 1 + 2 * T, lib.mmf_pf_forward_loop, C.byref(model_struct), T, N, M, _lib.ptr(states),
+            _lib.ptr(logw), _lib.ptr(controls), arr, _lib.ptr(modality_logw), enabled_mask, precision, _lib.ptr(eps),
+            estimation, mode, _lib.ptr(uniforms), _lib.ptr(rowbias), _lib.ptr(states_ws), _lib.ptr(logw_ws), _lib.ptr(est),
+            _lib.ptr(ws), _lib.stream_of(states),
+        )
+    )
+    return est
 
 
 def _resample_workspace(N, M, device):

@@ -289,17 +289,55 @@ class ParticleFilter(Filter):
 
     def forward_loop_hoisted(self, feats, modw, controls) -> torch.Tensor:
         """The recursion proper, given the per-head observation features (T, N, F_k) and modality log-weights
-        (T, N, K) of ``hoist_observations``: CUDA-graph replay for small problems, one kernel sequence per step
-        otherwise."""
+        (T, N, K) of ``hoist_observations``: CUDA-graph replay for small problems, otherwise ONE C call that enqueues the
+        per-trajectory rows of all steps plus two kernels per step (``mmf_pf_forward_loop``); the per-step path remains
+        for what that call does not cover (debug capture, soft resampling, a changing particle count)."""
         T, N = controls.shape[:2]
         replayed = self._forward_loop_graph(feats, modw, controls, T, N)
         if replayed is not None:
             return replayed
+        whole = self._forward_loop_whole(feats, modw, controls, T, N)
+        if whole is not None:
+            return whole
         estimates = controls.new_zeros((T, N, self.state_dim), dtype=torch.float32)
         for t in range(T):
             hoisted = ([None if f is None else f[t] for f in feats], None if modw is None else modw[t])
             estimates[t] = self.forward(observations=None, controls=controls[t], _hoisted=hoisted)
         return estimates
+
+    def _forward_loop_whole(self, feats, modw, controls, T, N):
+        """``mmf_pf_forward_loop``: returns the estimates, or None when the per-step path has to run."""
+        resample, mode = self._modes()
+        M = self.particle_states.shape[1]
+        if (
+            self.debug is not None or T == 0 or controls.dtype != torch.float32
+            or self.num_particles != M or (resample and self.soft_resample_alpha < 1.0)
+            or self.precision not in ops.PRECISIONS
+        ):
+            return None
+        plan = self.fused_plan()
+        sd = self.state_dim
+        like = self.particle_states
+        with torch.no_grad():
+            plan.refresh(like.device)
+            if self.noise is not None:  # injected draws: same per-step protocol as the step-by-step path
+                eps = torch.stack([self._process_eps(N * M, sd, like) for _ in range(T)])
+                uniforms = torch.stack([self._uniforms(N, M, like, mode) for _ in range(T)]) if resample else None
+            else:
+                eps = torch.randn((T, N * M, sd), device=like.device, dtype=torch.float32)
+                uniforms = None
+                if resample:
+                    shape = (T, N) if ops.is_systematic(mode) else (T, N, M)
+                    uniforms = torch.rand(shape, device=like.device, dtype=torch.float64)
+            states = like.detach().clone()  # the reference rebinds particle_states every step: never mutate the caller's tensor
+            logw = self.particle_log_weights.detach().clone()
+            est = ops.pf_forward_loop(
+                plan.struct, states, logw, controls, feats, modw, plan.enabled_mask(), eps,
+                precision=ops.PRECISIONS[self.precision], estimation=ops.ESTIMATION[self.estimation_method], mode=mode,
+                uniforms=uniforms,
+            )
+        self.particle_states, self.particle_log_weights = states, logw
+        return est
 
     def _forward_loop_graph(self, feats, modw, controls, T, N):
         """CUDA-graph replay of the hoisted T-step recursion.  Returns the estimates,
@@ -344,10 +382,14 @@ class ParticleFilter(Filter):
             try:
                 self.particle_states, self.particle_log_weights = st["states0"], st["logw0"]
                 with torch.cuda.graph(graph):
-                    for t in range(T):
-                        hoisted = ([None if f is None else f[t] for f in st["feats"]],
-                                   None if st["modw"] is None else st["modw"][t])
-                        st["est"][t] = self.forward(observations=None, controls=st["controls"][t], _hoisted=hoisted)
+                    whole = self._forward_loop_whole(st["feats"], st["modw"], st["controls"], T, N)
+                    if whole is not None:  # 1 + 2 T kernels + the two noise draws
+                        st["est"] = whole
+                    else:
+                        for t in range(T):
+                            hoisted = ([None if f is None else f[t] for f in st["feats"]],
+                                       None if st["modw"] is None else st["modw"][t])
+                            st["est"][t] = self.forward(observations=None, controls=st["controls"][t], _hoisted=hoisted)
                 st["statesT"], st["logwT"] = self.particle_states, self.particle_log_weights
                 # kernels recorded into the graph: they run at every replay, not during capture
                 st["launches"] = ops.PROFILE.launches - launches_before

@@ -679,3 +679,49 @@ def test_forward_loop_cuda_graph_replay_matches_eager():
     # the estimates agree statistically in any case, and bit for bit when the draws coincide
     assert_close(outs[0][0].cpu(), eager.cpu(), 1e-6, msg="eager twice")
     assert float((outs[1][0] - eager).abs().max()) < 1.0
+
+
+def test_weight_gradients_are_bit_reproducible():
+    """SURVEY.md section 7 hard part 4: the parameter-gradient reductions use no floating-point atomics (per-CTA partial
+    sums + a fixed-order second pass), so repeated launches on the same inputs agree bit for bit -- at a row count that
+    spreads over every CTA of the grid, and through a whole fused BPTT step."""
+    K, L, P, sd = 2, 7, 8192 * 30, 2
+    g = torch.Generator(device=DEV).manual_seed(5)
+    act = torch.randn(K, L + 1, 16, P, 4, device=DEV, generator=g)
+    delta = torch.randn(K, L + 1, 16, P, 4, device=DEV, generator=g)
+    x = torch.randn(P, sd, device=DEV, generator=g)
+    d_ll = torch.randn(K, P, device=DEV, generator=g)
+    first = [t.clone() for t in ops.pf_heads_weight_grads(act, delta, x, d_ll)]
+    for _ in range(3):
+        again = ops.pf_heads_weight_grads(act, delta, x, d_ll)
+        assert all(torch.equal(a, b) for a, b in zip(first, again))
+    # fp32 reference of the reductions (chunk-major planes -> row matrices)
+    A, D = ops.rows_view(act).double(), ops.rows_view(delta).double()
+    assert_close(first[0].cpu(), torch.einsum("klpj,klpi->klji", D[:, :L], A[:, :L]).cpu(), 2e-4, msg="dW")
+    assert_close(first[1].cpu(), D.sum(dim=2).cpu(), 2e-4, msg="db")
+    del act, delta, A, D
+
+    name, N, Mp, T = "PushCrossmodalParticleFilter", 64, 30, 4
+    init, eps, _ = draw_noise(T, N, Mp, sd, seed=51)
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=52)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd).to(DEV).contiguous()
+    runs = []
+    for _ in range(2):
+        f = fill_parameters(_product(name)(), seed=53).to(DEV).train()
+        f.num_particles = Mp
+        f.noise = ReplayNoise(init_eps=init, process_eps=eps)
+        for prm in f.dynamics_model.parameters():
+            prm.requires_grad_(False)
+        # the observation encoders are frozen here: cuDNN's convolution backward is outside this library's control
+        for h in f.measurement_model.measurement_models:
+            for prm in list(h.observation_image_layers.parameters()) if hasattr(h, "observation_image_layers") else []:
+                prm.requires_grad_(False)
+        for prm in f.measurement_model.crossmodal_weight_model.parameters():
+            prm.requires_grad_(False)
+        f.initialize_beliefs(mean=states[0].to(DEV), covariance=cov)
+        est = f.forward_loop(observations={k: v[1:].to(DEV) for k, v in obs.items()}, controls=controls[1:].to(DEV))
+        torch.mean((est - states[1:].to(DEV)) ** 2).backward()
+        runs.append({k: q.grad.clone() for k, q in f.named_parameters() if q.grad is not None})
+    assert len(runs[0]) > 20 and set(runs[0]) == set(runs[1])
+    differing = [k for k in runs[0] if not torch.equal(runs[0][k], runs[1][k])]
+    assert not differing, f"gradients differ between two identical runs: {differing[:5]}"

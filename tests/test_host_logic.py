@@ -29,7 +29,7 @@ def test_shared_library_exports_every_declared_symbol():
     assert not missing, missing
     lib = ctypes.CDLL(_lib.LIB_PATH)  # loads without a GPU; no compute call is made here
     lib.mmf_abi_version.restype = ctypes.c_int
-    assert lib.mmf_abi_version() == 1
+    assert lib.mmf_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_contains_only_sm100a_code():

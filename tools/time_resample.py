@@ -7,7 +7,7 @@ N, M, sd = int(os.environ.get("N", 4096)), int(os.environ.get("M", 1000)), 2
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
 states = torch.randn(N, M, sd, device=dev, generator=g)
-logw = torch.randn(N, M, device=dev, generator=g) * 3
+logw = torch.randn(N, M, device=dev, generator=g) * float(os.environ.get('SPREAD', 1.0))
 u_m = torch.rand(N, M, device=dev, dtype=torch.float64, generator=g)
 u_s = torch.rand(N, device=dev, dtype=torch.float64, generator=g)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -5,7 +5,10 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from multimodalfilter_b200 import ops
+from multimodalfilter_b200 import _lib, ops
+
+if os.environ.get("MMF_LIB"):  # measurement builds (make -C multimodalfilter_b200/csrc ablate)
+    _lib.LIB_PATH = os.path.abspath(os.environ["MMF_LIB"])
 from multimodalfilter_b200.crossmodal import models as M
 from multimodalfilter_b200.synthetic import fill_parameters
 
