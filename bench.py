@@ -586,6 +586,15 @@ def main():
     # inputs per pass (>= 100 MB of particle state + features) exceed nothing like L2 reuse across passes:
     # every step rewrites the N*M particle set (C3: 49 MB states+weights per step, new noise each step).
     ms_resident, clocks, prof = timed(resident_pass, args.steps, args.warmup, profile=True)
+    # kernel-level numbers: the same kernels launched step by step (one C call per kernel, CUDA events around each on the
+    # launching stream) instead of through the whole-sequence call, which offers no place to put an event
+    ms_profiled = None
+    if is_pf:
+        filt.whole_loop = False
+        saved_graph, filt.graph_max_particles = filt.graph_max_particles, 0
+        ms_profiled, _, prof_k = timed(resident_pass, max(1, min(args.steps, 2)), 1, profile=True)
+        filt.whole_loop, filt.graph_max_particles = True, saved_graph
+        prof["kernels"].update(prof_k["kernels"])
     # same step / warm-up counts as `value` (small workloads capture their CUDA graph on the second call: warm-up)
     ms_e2e, clocks_e2e, _ = timed(e2e_pass, args.steps, args.warmup)
 
@@ -633,9 +642,12 @@ def main():
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                 "traffic": ncu_traffic("prof_chain_tc") if args.workload == "c3" else None, "traffic_unit": "dram bytes per launch (ncu --set full, C3 step)",
                 "peak_source": f"{peaks['source']} bf16 sustained", "avg_launch_ms": k["avg_ms"],
-                "share_of_step": k["total_ms"] / (ms_resident * args.steps),
-                "other_kernels": {n: {"avg_ms": v["avg_ms"], "share": v["total_ms"] / (ms_resident * args.steps)}
-                                  for n, v in prof["kernels"].items() if n != "pf_predict_measure"},
+                "share_of_step": k["avg_ms"] * T / ms_resident,
+                "timed_in": "a pass that launches the kernels step by step (CUDA events per launch); value / ms_per_step "
+                            "come from the whole-sequence call (mmf_pf_forward_loop)", "ms_per_step_profiled_pass": ms_profiled,
+                "other_kernels": {n: {"avg_ms": v["avg_ms"], "count_per_pass": v["count"] / max(1, min(args.steps, 2)),
+                                      "share": v["avg_ms"] * v["count"] / max(1, min(args.steps, 2)) / ms_resident}
+                                  for n, v in prof["kernels"].items() if n not in ("pf_predict_measure", "pf_forward_loop")},
             }
             nr = prof["kernels"].get("pf_normalize_resample")
             if nr:

@@ -287,6 +287,31 @@ int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, int32_t sd, co
                               const float* x, const float* d_ll, float* dW_out, float* db_out, float* g_in_out,
                               float* g_out_out, void* workspace, void* stream);
 
+/* Per-trajectory MLP stacks (observation encoders of positions / sensors, crossmodal weight models, virtual-sensor heads:
+ * ref: crossmodal/push_models/layers.py:107-136, crossmodal/push_models/crossmodal_pf.py:72-104,
+ * crossmodal/door_models/crossmodal_kf.py:134-167, crossmodal/door_models/kf.py:81-126) as ONE launch: the host
+ * compiles the nn.Sequential into a program of fused ops over per-row scratch slots,
+ *     scratch[dst : dst + out_dim] = act(W scratch[src : src + in_dim] + b [+ scratch[res : res + out_dim]])
+ * with W stored input-major, Wt[in_dim][out_dim], followed by b[out_dim], at float offset `w_off` of `weights`.
+ * A resblock is two ops (the second with res = the block's input).  `inputs[i]` (rows, in_dims[i]) is copied to slot
+ * in_slots[i] before the program; `outputs[i]` (rows, out_dims[i]) is read from slot out_slots[i] after it.
+ * `ops`, `inputs`, `outputs` and the dims / slots arrays are HOST arrays; `weights` and the tensors are device memory.
+ * dst must not overlap src or res.  fp32 FFMA, inputs summed in index order. */
+#define MMF_MLP_MAX_OPS 24
+#define MMF_MLP_MAX_IO 4
+#define MMF_MLP_NONE 0
+#define MMF_MLP_RELU 1
+#define MMF_MLP_SIGMOID 2
+typedef struct mmf_mlp_op {
+  int32_t in_dim, out_dim, act;
+  int32_t src, dst, res; /* scratch slots (float offsets); res < 0: no residual */
+  int64_t w_off;
+} mmf_mlp_op;
+int mmf_row_mlp(int64_t rows, const mmf_mlp_op* ops, int32_t n_ops, const float* weights, const float* const* inputs,
+                const int32_t* in_dims, const int32_t* in_slots, int32_t n_inputs, float* const* outputs,
+                const int32_t* out_dims, const int32_t* out_slots, int32_t n_outputs, int32_t scratch_floats,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

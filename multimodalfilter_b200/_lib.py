@@ -66,6 +66,18 @@ class EKFModel(C.Structure):
     ]
 
 
+class MlpOp(C.Structure):
+    _fields_ = [
+        ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("act", C.c_int32),
+        ("src", C.c_int32), ("dst", C.c_int32), ("res", C.c_int32),
+        ("w_off", C.c_int64),
+    ]
+
+
+MLP_MAX_OPS, MLP_MAX_IO = 24, 4
+MLP_NONE, MLP_RELU, MLP_SIGMOID = 0, 1, 2
+
+
 class MMFError(RuntimeError):
     pass
 
@@ -115,6 +127,11 @@ PROTOTYPES = {
     "mmf_enc_trunk": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mmf_enc_stem": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "mmf_enc_conv3x3": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "mmf_row_mlp": (
+        C.c_int,
+        [C.c_int64, C.POINTER(MlpOp), _i32, _vp, C.POINTER(_vp), C.POINTER(_i32), C.POINTER(_i32), _i32, C.POINTER(_vp),
+         C.POINTER(_i32), C.POINTER(_i32), _i32, _i32, _vp],
+    ),
     "mmf_chain_mma_bytes": (_sz, [C.POINTER(Chain)]),
     "mmf_pack_chain_mma": (C.c_int, [C.POINTER(Chain), _vp, _vp]),
 }

@@ -81,6 +81,44 @@ class _Encoders(nn.Module):
                 parts.append(getattr(self, attr)(x[:, None] if mod == "image" else x))
         return torch.cat(parts, dim=1)
 
+    def _encoder_list(self):
+        return [(mod, getattr(self, attr)) for mod, attr in fused.OBS_ORDER if mod in self.modalities]
+
+    def encoded_program(self, key, tails, units=UNITS):
+        """One ``mmf_row_mlp`` program for "encode the non-image modalities, concatenate, run the tail stacks":
+        ``tails`` = list of (nn.Sequential, column offset into the first tail's output or None for the concatenated
+        features, input width); each tail's result is an output.  Image features are an input (CNN trunk kernel +
+        Linear tail run as the module).  Cached per module; None when a stack is not fusable."""
+        def build():
+            prog = fused.RowProgram()
+            encs = self._encoder_list()
+            base = prog.alloc(units * len(encs))
+            for i, (mod, enc) in enumerate(encs):
+                if mod == "image":
+                    prog.input(units, slot=base + units * i)
+                else:
+                    src = prog.input(enc[0].in_features)
+                    prog.sequential(enc, src, enc[0].in_features, dst=base + units * i)
+            first = None
+            for seq, offset, width in tails:
+                src = base if offset is None else first + offset
+                slot, dim = prog.sequential(seq, src, width)
+                first = slot if first is None else first
+                if offset is not None or len(tails) == 1:
+                    prog.output(slot, dim)
+            return prog
+
+        return fused.cached_program(self, key, build)
+
+    def program_inputs(self, observations):
+        """Inputs of ``encoded_program`` in its order, or None when the fused launch does not apply."""
+        encs = self._encoder_list()
+        raw = [observations[fused.OBS_KEY[mod]] for mod, _ in encs if mod != "image"]
+        if not fused.row_program_ok(*raw) or ("image" in self.modalities and not observations["image"].is_cuda):
+            return None
+        return [enc(observations["image"][:, None]) if mod == "image" else observations[fused.OBS_KEY[mod]]
+                for mod, enc in encs]
+
 
 def _blackout_rows(observations):
     img = observations["image"]
@@ -236,7 +274,9 @@ class _PFWeights(CrossmodalWeightModel, _Encoders):
         )
 
     def forward(self, *, observations):
-        out = self.fusion_layers(self.encode(observations))
+        ins = self.program_inputs(observations)
+        prog = self.encoded_program("weights", [(self.fusion_layers, None, 3 * UNITS)]) if ins is not None else None
+        out = prog.run(ins)[0] if prog is not None else self.fusion_layers(self.encode(observations))
         assert out.shape == (observations["gripper_pos"].shape[0], self.modality_count)
         if self.know_image_blackout:
             out[_blackout_rows(observations), 0] -= np.inf  # quirk Q3
@@ -318,9 +358,17 @@ class _VirtualSensor(tf_base.VirtualSensorModel, _Encoders):
     def forward(self, *, observations):
         # R9, ref: crossmodal/door_models/kf.py:81-126
         assert type(observations) == dict
-        h = self.shared_layers(self.encode(observations))
-        z = self.z_layer(h[:, : self.units].clone())
-        lt_hat = self.r_layer(h[:, self.units :].clone()) if self.noise_R_tril is None else self.noise_R_tril
+        ins = self.program_inputs(observations) if self.noise_R_tril is None else None
+        prog = None
+        if ins is not None:  # encoders + shared stack + both heads in one launch (mmf_row_mlp)
+            prog = self.encoded_program("sensor", [(self.shared_layers, None, self.units * len(self.modalities)),
+                                                   (self.z_layer, 0, self.units), (self.r_layer, self.units, self.units)])
+        if prog is not None:
+            z, lt_hat = prog.run(ins)
+        else:
+            h = self.shared_layers(self.encode(observations))
+            z = self.z_layer(h[:, : self.units].clone())
+            lt_hat = self.r_layer(h[:, self.units :].clone()) if self.noise_R_tril is None else self.noise_R_tril
         R = torch.diag_embed(lt_hat) ** 2
         if self.add_R_noise[0] > 0:
             R = R + torch.diag(self.add_R_noise).to(R.device)
@@ -380,6 +428,10 @@ class _KFWeights(CrossmodalKalmanFilterWeightModel, _Encoders):
         self.know_image_blackout = know_image_blackout
 
     def raw(self, observations):
+        ins = self.program_inputs(observations)
+        prog = self.encoded_program("weights", [(self.fusion_layers, None, 3 * UNITS)]) if ins is not None else None
+        if prog is not None:  # encoders + fusion stack + sigmoid in one launch
+            return prog.run(ins)[0]
         return self.fusion_layers(self.encode(observations))
 
     @staticmethod

@@ -348,6 +348,16 @@ int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, int32_t sd, co
                          (cudaStream_t)stream);
 }
 
+int mmf_row_mlp(int64_t rows, const mmf_mlp_op* ops, int32_t n_ops, const float* weights, const float* const* inputs,
+                const int32_t* in_dims, const int32_t* in_slots, int32_t n_inputs, float* const* outputs,
+                const int32_t* out_dims, const int32_t* out_slots, int32_t n_outputs, int32_t scratch_floats,
+                void* stream) {
+  MMF_REQUIRE(rows >= 0, "row_mlp: rows = %lld", (long long)rows);
+  MMF_REQUIRE(inputs && in_dims && in_slots && outputs && out_dims && out_slots, "row_mlp: NULL argument array");
+  return launch_row_mlp(rows, ops, n_ops, weights, inputs, in_dims, in_slots, n_inputs, outputs, out_dims, out_slots,
+                        n_outputs, scratch_floats, (cudaStream_t)stream);
+}
+
 size_t mmf_enc_map_bytes(int32_t channels) { return enc_map_bytes_host(channels); }
 
 int mmf_enc_stem(int32_t n_images, const float* images, const float* w, void* out_map, void* stream) {

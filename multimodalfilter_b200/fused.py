@@ -200,8 +200,31 @@ class _HeadSpec:
         (_, pre), (_, post, _) = self.state, self.shared
         return _chain_struct(chain, self.sd, len(pre), True, len(post), 1), _rows_struct(rows, self.feat_dim, False)
 
+    def _feature_program(self):
+        """Encoders of the non-image modalities + the concatenation as one mmf_row_mlp launch; the image features
+        (CNN trunk kernel + Linear tail) enter as an input."""
+        prog = RowProgram()
+        base = prog.alloc(self.feat_dim)
+        for i, (key, enc) in enumerate(self.encoders):
+            if key == "image":
+                prog.input(U, slot=base + U * i)
+            else:
+                src = prog.input(enc[0].in_features)
+                prog.sequential(enc, src, enc[0].in_features, dst=base + U * i)
+        prog.output(base, self.feat_dim)
+        return prog
+
     def observation_features(self, observations) -> torch.Tensor:
         """(B, feat_dim) for a dict of (B, ...) observations (ref: pf.py:76-88, order image/pos/sensors)."""
+        raw = [observations[key] for key, _ in self.encoders if key != "image"]
+        if raw and row_program_ok(*raw):
+            prog = cached_program(self.head, "features", self._feature_program)
+            if prog is not None:
+                ins = []
+                for key, enc in self.encoders:
+                    x = observations[key]
+                    ins.append(enc(x[:, None, :, :]) if key == "image" else x)
+                return prog.run(ins)[0]
         feats = []
         for key, enc in self.encoders:
             x = observations[key]
@@ -370,6 +393,113 @@ class EKFPlan:
     def jacobian(self, which, states, controls):
         self.refresh(states.device)
         return ops.dynamics_jacobian(self.structs[which], states, controls)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-trajectory MLP stacks -> one-launch programs (mmf_row_mlp)
+# ------------------------------------------------------------------------------------------------
+class NotFusable(Exception):
+    pass
+
+
+class RowProgram:
+    """A stack of Linear / ReLU / Sigmoid / fannypack resblocks over per-trajectory rows, compiled for ``mmf_row_mlp``:
+    a list of fused ops ``dst = act(W src + b [+ res])`` over scratch slots (float offsets into a per-row scratch),
+    the input-major weight pack, and the input / output slots.  Build with ``input`` / ``sequential`` / ``output``;
+    ``run`` repacks the weights when a parameter changed."""
+
+    def __init__(self):
+        self.ops, self.params, self._w_floats, self.scratch = [], [], 0, 0
+        self.in_slots, self.in_dims, self.out_slots, self.out_dims = [], [], [], []
+        self._packed = None
+
+    def alloc(self, dim: int) -> int:
+        slot, self.scratch = self.scratch, self.scratch + ((dim + 3) // 4) * 4
+        return slot
+
+    def input(self, dim: int, slot: int = None) -> int:
+        slot = self.alloc(dim) if slot is None else slot
+        self.in_slots.append(slot)
+        self.in_dims.append(dim)
+        return slot
+
+    def output(self, slot: int, dim: int) -> None:
+        self.out_slots.append(slot)
+        self.out_dims.append(dim)
+
+    def _linear(self, lin: nn.Linear, src: int, act: int, res: int = -1, dst: int = None) -> int:
+        if lin.bias is None or lin.out_features > 256:
+            raise NotFusable("Linear without bias or wider than 256")
+        dst = self.alloc(lin.out_features) if dst is None else dst
+        op = _lib.MlpOp()
+        op.in_dim, op.out_dim, op.act, op.src, op.dst, op.res, op.w_off = (
+            lin.in_features, lin.out_features, act, src, dst, res, self._w_floats)
+        self.ops.append(op)
+        self.params.append(lin)
+        self._w_floats += lin.in_features * lin.out_features + lin.out_features
+        if len(self.ops) > _lib.MLP_MAX_OPS:
+            raise NotFusable("program too long")
+        return dst
+
+    def sequential(self, seq, src: int, src_dim: int, dst: int = None):
+        """Append the modules of an nn.Sequential (or a list); the LAST op writes to ``dst`` when given.
+        Returns (slot, dim) of the result."""
+        mods = list(seq)
+        cur, dim, i = src, src_dim, 0
+        while i < len(mods):
+            m = mods[i]
+            last = lambda consumed: i + consumed >= len(mods)  # noqa: E731
+            if isinstance(m, nn.Linear):
+                if m.in_features != dim:
+                    raise NotFusable("width mismatch")
+                act, used = _lib.MLP_NONE, 1
+                if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                    act, used = _lib.MLP_RELU, 2
+                elif i + 1 < len(mods) and isinstance(mods[i + 1], nn.Sigmoid):
+                    act, used = _lib.MLP_SIGMOID, 2
+                cur = self._linear(m, cur, act, dst=dst if last(used) else None)
+                dim, i = m.out_features, i + used
+            elif isinstance(getattr(m, "block1", None), nn.Linear) and isinstance(getattr(m, "block2", None), nn.Linear):
+                act = getattr(m, "activation", None)
+                if (act is not None and not isinstance(act, nn.ReLU)) or m.block1.in_features != dim \
+                        or m.block2.out_features != dim or m.block1.out_features != m.block2.in_features:
+                    raise NotFusable("unsupported residual block")
+                t = self._linear(m.block1, cur, _lib.MLP_RELU)
+                cur = self._linear(m.block2, t, _lib.MLP_RELU, res=cur, dst=dst if last(1) else None)
+                i += 1
+            else:
+                raise NotFusable(f"unsupported module {type(m).__name__}")
+        return cur, dim
+
+    def _weights(self, device):
+        sig = (str(device), tuple((p.data_ptr(), p._version) for lin in self.params for p in (lin.weight, lin.bias)))
+        if self._packed is None or self._packed[0] != sig:
+            parts = []
+            for lin in self.params:
+                parts += [lin.weight.detach().t().contiguous().reshape(-1), lin.bias.detach().reshape(-1)]
+            self._packed = (sig, torch.cat([p.float() for p in parts]).to(device).contiguous())
+        return self._packed[1]
+
+    def run(self, inputs):
+        assert len(inputs) == len(self.in_slots) and all(x.shape[1] == d for x, d in zip(inputs, self.in_dims))
+        return ops.row_mlp(self.ops, self._weights(inputs[0].device), inputs, self.in_slots, self.out_dims, self.out_slots,
+                           self.scratch)
+
+
+def row_program_ok(*tensors) -> bool:
+    """The one-launch programs serve inference on CUDA fp32 rows; anything else keeps the torch modules."""
+    return not torch.is_grad_enabled() and all(t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 for t in tensors)
+
+
+def cached_program(owner, key, build):
+    """Per-module cache of compiled programs (None = the stack is not fusable: keep the torch path)."""
+    cache = owner.__dict__.setdefault("_mmf_programs", {})
+    if key not in cache:
+        try:
+            cache[key] = build()
+        except NotFusable:
+            cache[key] = None
+    return cache[key]
 
 
 def flatten_time(observations, T, N):

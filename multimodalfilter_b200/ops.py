@@ -268,6 +268,30 @@ def enc_trunk(images, weights, scratch, cout):
     return out
 
 
+def row_mlp(program_ops, weights, inputs, in_slots, out_dims, out_slots, scratch):
+    """One launch of a compiled per-trajectory MLP program (``fused.RowProgram``): inputs are (rows, d_i) fp32 tensors,
+    returns the list of (rows, out_dims[i]) outputs."""
+    lib = _lib.load()
+    rows = inputs[0].shape[0]
+    inputs = [_f32c(x) for x in inputs]
+    assert all(x.dim() == 2 and x.shape[0] == rows for x in inputs)
+    dev = inputs[0].device
+    outs = [torch.empty((rows, d), device=dev, dtype=torch.float32) for d in out_dims]
+    n_ops, n_in, n_out = len(program_ops), len(inputs), len(outs)
+    op_arr = (_lib.MlpOp * n_ops)(*program_ops)
+    in_ptrs = (C.c_void_p * n_in)(*[x.data_ptr() for x in inputs])
+    in_dims = (C.c_int32 * n_in)(*[x.shape[1] for x in inputs])
+    in_sl = (C.c_int32 * n_in)(*in_slots)
+    out_ptrs = (C.c_void_p * n_out)(*[o.data_ptr() for o in outs])
+    out_d = (C.c_int32 * n_out)(*out_dims)
+    out_sl = (C.c_int32 * n_out)(*out_slots)
+    for x in inputs:  # devices of the buffers whose pointers travel in arrays
+        _lib.ptr(x)
+    _lib.check(PROFILE.run("row_mlp", 1, lib.mmf_row_mlp, rows, op_arr, n_ops, _lib.ptr(weights), in_ptrs, in_dims, in_sl,
+                           n_in, out_ptrs, out_d, out_sl, n_out, scratch, _lib.stream_of(inputs[0])))
+    return outs
+
+
 def pf_init(mean, covariance, eps_MNsd):
     """R2: (N,sd), (N,sd,sd), (M,N,sd) -> particle_states (N,M,sd), particle_log_weights (N,M)."""
     lib = _lib.load()

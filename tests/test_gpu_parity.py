@@ -725,3 +725,40 @@ def test_weight_gradients_are_bit_reproducible():
     assert len(runs[0]) > 20 and set(runs[0]) == set(runs[1])
     differing = [k for k in runs[0] if not torch.equal(runs[0][k], runs[1][k])]
     assert not differing, f"gradients differ between two identical runs: {differing[:5]}"
+
+
+@pytest.mark.parametrize("rows", [1, 37, 4099])
+def test_row_mlp_programs_match_torch_modules(rows):
+    """mmf_row_mlp (one launch per per-trajectory stack) against the same modules evaluated by torch: observation
+    encoders + concatenation of a head, PF / KF crossmodal weight models, virtual-sensor heads."""
+    from multimodalfilter_b200.synthetic import synthetic_trajectories as synth
+
+    _, obs, _ = synth(1, rows, 3, seed=61)
+    o = {k: v[0].to(DEV) for k, v in obs.items()}
+    cases = [
+        ("head features", fill_parameters(M.PushCrossmodalParticleFilter(), seed=62).to(DEV).eval()),
+        ("PF weights push", fill_parameters(M.PushCrossmodalWeightModel(know_image_blackout=False), seed=63).to(DEV).eval()),
+        ("PF weights door", fill_parameters(M.DoorCrossmodalWeightModel(know_image_blackout=True), seed=64).to(DEV).eval()),
+        ("KF weights", fill_parameters(M.DoorCrossmodalKalmanFilterWeightModel(state_dim=3), seed=65).to(DEV).eval()),
+        ("virtual sensor door", fill_parameters(M.DoorVirtualSensorModel(), seed=66).to(DEV).eval()),
+        ("virtual sensor push force", fill_parameters(M.PushVirtualSensorModel(modalities={"pos", "sensors"}), seed=67).to(DEV).eval()),
+        ("virtual sensor push image", fill_parameters(M.PushVirtualSensorModel(modalities={"image"}), seed=68).to(DEV).eval()),
+    ]
+    for name, mod in cases:
+        ops.PROFILE.reset(enabled=True)
+        if name == "head features":
+            plan = fused.PFPlan.build(mod)
+            with torch.no_grad():
+                got = [h.observation_features(o) for h in plan.heads]
+            with torch.enable_grad():  # the torch-module path
+                ref = [h.observation_features(o).detach() for h in plan.heads]
+        else:
+            with torch.no_grad():
+                got = mod(observations=o)
+            with torch.enable_grad():
+                ref = mod(observations=o)
+            got, ref = (list(got), [r.detach() for r in ref]) if isinstance(got, tuple) else ([got], [ref.detach()])
+        assert "row_mlp" in ops.PROFILE.collect()["kernels"], f"{name}: mmf_row_mlp did not run"
+        ops.PROFILE.reset()
+        for g_, r_ in zip(got, ref):
+            assert_close(g_.cpu(), r_.cpu(), 2e-5, msg=name)
