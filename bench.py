@@ -276,7 +276,12 @@ def run_c4(ctx, steps, warmup, precision):
     for p in trainable:
         p.requires_grad_(True)
     grads = FlatGradients(trainable)
-    reduce_ = StreamAllReduce(dev)
+    # The step's only collective.  Default at N > 1: the step is TWO CUDA graphs (zero + forward + backward | scale + Adam)
+    # with torch.distributed's NCCL all-reduce of the flat gradient buffer enqueued between them on the same stream.
+    # MMF_NCCL_IN_GRAPH=1 (opt-in): ncclAllReduce issued on the capture stream (distributed.StreamAllReduce), the whole
+    # step one graph.
+    in_graph = world > 1 and os.environ.get("MMF_NCCL_IN_GRAPH") == "1"
+    reduce_ = StreamAllReduce(dev) if in_graph else None
     # fused: one multi-tensor kernel instead of ~10 launches per tensor; capturable: the step lives in a CUDA graph
     opt = torch.optim.Adam(trainable, lr=1e-4, fused=True, capturable=True)
     g = torch.Generator(device=dev).manual_seed(rank)
@@ -287,7 +292,7 @@ def run_c4(ctx, steps, warmup, precision):
     mean0 = torch.randn(N, sd, device=dev, generator=g)
     cov = (torch.eye(sd, device=dev) * 0.1)[None].expand(N, sd, sd).contiguous()
 
-    def step():
+    def forward_backward():
         grads.zero()
         filt.initialize_beliefs(mean=mean0, covariance=cov)
         ests = []
@@ -296,8 +301,23 @@ def run_c4(ctx, steps, warmup, precision):
             ests.append(filt.forward(observations=None, controls=controls[t], _hoisted=([feats[0][t], feats[1][t]], modw)))
         loss = torch.mean((torch.stack(ests) - targets) ** 2)
         loss.backward()
-        reduce_(grads.flat)  # the step's only collective, on this stream, between backward and Adam
+        if in_graph:
+            reduce_(grads.flat)  # ncclAllReduce (avg) on this stream
+        return loss
+
+    def exchange():  # between the two graphs: the process group's all-reduce, stream-ordered after backward
+        if world > 1 and not in_graph:
+            dist.all_reduce(grads.flat, op=dist.ReduceOp.SUM)
+
+    def update():
+        if world > 1 and not in_graph:
+            grads.flat.mul_(1.0 / world)
         opt.step()
+
+    def step():
+        loss = forward_backward()
+        exchange()
+        update()
         return loss
 
     def barrier():
@@ -322,14 +342,27 @@ def run_c4(ctx, steps, warmup, precision):
         prof = ops.PROFILE.collect()
         ops.PROFILE.reset(enabled=False)
         eager_ms = e0.elapsed_time(e1)
+        graph2 = None
         if not os.environ.get("MMF_BENCH_NO_GRAPH"):
             try:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side):
-                    static_loss = step()
+                    static_loss = forward_backward()
+                    if world == 1 or in_graph:
+                        update()
+                if world > 1 and not in_graph:
+                    graph2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph2, stream=side):
+                        update()
                 graph.replay()  # first replay outside the timed region
+                if graph2 is not None:
+                    exchange()
+                    graph2.replay()
                 side.synchronize()
-                launch = "one CUDA graph per training step (all-reduce inside)" if world > 1 else "one CUDA graph per training step"
+                launch = ("one CUDA graph per training step" if world == 1 else
+                          "one CUDA graph per training step (ncclAllReduce inside)" if in_graph else
+                          "two CUDA graphs per training step (zero + forward + backward | scale + Adam), the NCCL all-reduce "
+                          "enqueued between them on the same stream")
             except Exception as exc:
                 print(f"[bench] rank {rank}: CUDA-graph capture of the training step failed ({type(exc).__name__}: {exc})",
                       file=sys.stderr, flush=True)
@@ -345,6 +378,9 @@ def run_c4(ctx, steps, warmup, precision):
         for _ in range(steps):
             if graph is not None:
                 graph.replay()
+                if graph2 is not None:
+                    exchange()
+                    graph2.replay()
             else:
                 loss = step()
         if graph is not None:
@@ -364,14 +400,18 @@ def run_c4(ctx, steps, warmup, precision):
                    "encoders": "hoisted and frozen (features are inputs)", "final_loss": float(loss.detach()),
                    "launch": launch, "eager_ms_per_step": eager_ms,
                    "allreduce": {"elements": int(grads.flat.numel()), "bytes": int(grads.flat.numel()) * 4,
-                                 "ranks": world, "how": "ncclAllReduce (avg, fp32, in place on the flat gradient buffer) "
-                                                        "on the step's stream" if world > 1 else "none (1 rank)"}},
+                                 "ranks": world, "how": ("none (1 rank)" if world == 1 else
+                                                        "ncclAllReduce (avg, fp32, in place on the flat gradient buffer) "
+                                                        "captured on the step's stream" if in_graph else
+                                                        "torch.distributed NCCL all_reduce (sum, fp32, in place on the flat "
+                                                        "gradient buffer) between the step's two graphs")}},
         "clocks": clk.summary(), "gpu_launches": prof["launches"] * steps, "kernels": kern,
         "e2e": {"value": world * units / (ms / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 4, "note": "training step is device-resident; loss scalar read back"},
     }
-    reduce_.close()
-    del graph
+    if reduce_ is not None:
+        reduce_.close()
+    del graph, graph2
     return record
 
 
@@ -473,6 +513,9 @@ def main():
     ap.add_argument("--resample-mode", default="multinomial")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if os.environ.get("MMF_BENCH_WATCHDOG_S"):  # diagnosis of a hung rank: dump every thread's stack and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["MMF_BENCH_WATCHDOG_S"]), exit=True)
     assert args.warmup >= 3 or args.impl == "reference" or os.environ.get("MMF_BENCH_ALLOW_SHORT"), "W >= 3 warm-up steps"
 
     if args.impl == "reference":
@@ -627,9 +670,13 @@ def main():
         del feats, modw
         filt.particle_states = filt.particle_log_weights = None
         torch.cuda.empty_cache()
-        tr = run_c4(ctx, max(args.steps, 5), args.warmup, args.precision)
-        line["training"] = {k: tr[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "steps", "dtype", "config", "clocks")}
-        line["training"]["kernels"] = tr["kernels"]
+        try:
+            tr = run_c4(ctx, max(args.steps, 5), args.warmup, args.precision)
+            line["training"] = {k: tr[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "steps", "dtype", "config", "clocks")}
+            line["training"]["kernels"] = tr["kernels"]
+        except Exception as exc:  # the forward line above is measured: a failing training record must not take it down
+            print(f"[bench] rank {rank}: training record failed ({type(exc).__name__}: {exc})", file=sys.stderr, flush=True)
+            line["training"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0:
         peaks = measured_peaks()
         line["config"]["e2e_timing"] = "same steps / warm-up as value"

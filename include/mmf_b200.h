@@ -223,6 +223,16 @@ int mmf_kf_fuse_crossmodal(int32_t K, int32_t rows, int32_t sd, const float* mu,
 int mmf_kf_fuse_unimodal(int32_t K, int32_t rows, int32_t sd, const float* mu, const float* P,
                          float* mean_out, float* cov_out, void* stream);
 
+/* R12  measurement-level fusion of K virtual sensors (ref: crossmodal/base_models/crossmodal_kf.py:219-235,337-354
+ * CrossmodalVirtualSensorModel.forward; crossmodal/base_models/unimodal_kf.py:56-115 UnimodalVirtualSensorModel.forward):
+ * rows independent fusions, z (K,rows,sd), r_tril (K,rows,sd,sd) lower factors, weights (K,rows,sd) or NULL.
+ *   weights != NULL (crossmodal): z_out = sum_k (w_k / (sum_k w_k + 1e-9)) z_k ;
+ *                                 mat_out = cholesky((prod_k prod_d w_k[d]) * sum_k L_k L_k^T)          (a lower factor)
+ *   weights == NULL (unimodal):   K == 1: z_0 and L_0 L_0^T; else Pr_k = 1 / (L_k + 1e-9) elementwise, w_k = diag Pr_k,
+ *                                 z_out as above, mat_out = inverse(sum_k Pr_k + 1e-9)                  (a covariance) */
+int mmf_kf_fuse_measurements(int32_t K, int32_t rows, int32_t sd, const float* z, const float* r_tril, const float* weights,
+                             float* z_out, float* mat_out, void* stream);
+
 /* Build the tcgen05 operand pack of a chain (bf16 hi/lo copies of every 64x64 matrix in the
  * UMMA shared-memory layout).  dst must hold mmf_chain_mma_bytes(chain) bytes. */
 size_t mmf_chain_mma_bytes(const mmf_chain* chain);

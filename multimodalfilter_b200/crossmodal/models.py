@@ -465,6 +465,11 @@ def _mask_weights(flags, N, sd, device):  # ref: base_models/crossmodal_kf.py:12
     return w[:, None, None].repeat(1, N, sd)
 
 
+def _fuse_kernel_ok(*tensors) -> bool:
+    """mmf_kf_fuse_measurements serves inference on CUDA fp32 tensors; autograd keeps the torch expressions."""
+    return not torch.is_grad_enabled() and all(t.is_cuda and t.dtype == torch.float32 for t in tensors)
+
+
 def _measurement_level(states, trils, weights):  # ref: base_models/crossmodal_kf.py:219-235,337-354
     covs = trils @ trils.transpose(-1, -2)
     mult = torch.prod(torch.prod(weights, dim=-1), dim=0)[:, None, None]
@@ -660,6 +665,8 @@ class CrossmodalVirtualSensorModel(tf_base.VirtualSensorModel, _EnabledModels):
             weights = _mask_weights(on, N, self.state_dim, states.device)
         else:
             weights = self.crossmodal_weight_model(observations=observations)
+        if _fuse_kernel_ok(states, trils, weights):  # one launch: weighted mean, scaled covariance sum, Cholesky factor
+            return ops.kf_fuse_measurements(states, trils, weights[on])
         mean, cov = _measurement_level(states, trils, weights[on])
         return mean, torch.linalg.cholesky(cov)
 
@@ -675,6 +682,8 @@ class UnimodalVirtualSensorModel(tf_base.VirtualSensorModel, _EnabledModels):
     def forward(self, *, observations):
         outs = [m(observations=observations) for m, flag in zip(self.virtual_sensor_model, self._enabled_models) if flag]
         states, trils = torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
+        if _fuse_kernel_ok(states, trils):
+            return ops.kf_fuse_measurements(states, trils, None)
         covs = trils @ trils.transpose(-1, -2)
         if len(outs) == 1:
             return states[0], covs[0]

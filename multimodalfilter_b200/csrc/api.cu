@@ -282,6 +282,14 @@ int mmf_kf_fuse_crossmodal(int32_t K, int32_t rows, int32_t sd, const float* mu,
   return launch_kf_fuse(K, rows, sd, mu, P, beta, mean_out, cov_out, 0, (cudaStream_t)stream);
 }
 
+int mmf_kf_fuse_measurements(int32_t K, int32_t rows, int32_t sd, const float* z, const float* r_tril, const float* weights,
+                             float* z_out, float* mat_out, void* stream) {
+  MMF_REQUIRE(K >= 1 && rows >= 0 && sd >= 1 && sd <= MMF_MAX_SD, "kf_fuse_measurements: bad shape K=%d rows=%d sd=%d", K, rows, sd);
+  MMF_REQUIRE(rows == 0 || (z && r_tril && z_out && mat_out), "kf_fuse_measurements: NULL buffer");
+  return launch_kf_fuse_measurements(K, rows, sd, z, r_tril, weights, z_out, mat_out, weights == nullptr ? 1 : 0,
+                                     (cudaStream_t)stream);
+}
+
 int mmf_kf_fuse_unimodal(int32_t K, int32_t rows, int32_t sd, const float* mu, const float* P, float* mean_out,
                          float* cov_out, void* stream) {
   MMF_REQUIRE(K >= 1 && rows >= 0 && sd >= 1 && sd <= MMF_MAX_SD, "kf_fuse: bad shape K=%d rows=%d sd=%d", K, rows, sd);

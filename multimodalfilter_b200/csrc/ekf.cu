@@ -560,4 +560,127 @@ int launch_kf_fuse(int K, long long rows, int sd, const float* mu, const float* 
   return MMF_OK;
 }
 
+// ---- R12 measurement-level fusion of K virtual sensors: one thread per (t, n) row ---------------------------
+// crossmodal (ref: crossmodal/base_models/crossmodal_kf.py:219-235, 337-354, utility.py:4-11):
+//   z = sum_k (w_k / (sum_k w_k + 1e-9)) z_k ;  C = (prod_k prod_d w_k[d]) * sum_k L_k L_k^T ;  out = cholesky(C)
+// unimodal (ref: crossmodal/base_models/unimodal_kf.py:56-115; returns a covariance, as the reference does):
+//   K == 1: (z_0, L_0 L_0^T);  else  Pr_k = 1 / (L_k + 1e-9) ELEMENTWISE (the reference's arithmetic, zeros above the
+//   diagonal included), w_k = diag(Pr_k), z as above, out = inverse(sum_k Pr_k + 1e-9)
+template <int SD>
+__global__ void k_kf_fuse_measurements(int K, long long rows, const float* __restrict__ z, const float* __restrict__ tril,
+                                       const float* __restrict__ w, float* __restrict__ z_out,
+                                       float* __restrict__ mat_out, int unimodal) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    float wsum[SD], mean[SD], acc[SD][SD], out[SD][SD];
+    float mult = 1.0f;
+#pragma unroll
+    for (int d = 0; d < SD; ++d) {
+      wsum[d] = 0.0f;
+      mean[d] = 0.0f;
+#pragma unroll
+      for (int e = 0; e < SD; ++e) acc[d][e] = 0.0f;
+    }
+    auto weight = [&](int k, int d) -> float {
+      if (!unimodal) return w[((size_t)k * rows + r) * SD + d];
+      return 1.0f / (tril[(((size_t)k * rows + r) * SD + d) * SD + d] + 1e-9f);
+    };
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int d = 0; d < SD; ++d) {
+        const float wk = weight(k, d);
+        wsum[d] += wk;
+        mult *= wk;
+      }
+    for (int k = 0; k < K; ++k) {
+      float L[SD][SD];
+#pragma unroll
+      for (int d = 0; d < SD; ++d)
+#pragma unroll
+        for (int e = 0; e < SD; ++e) L[d][e] = tril[(((size_t)k * rows + r) * SD + d) * SD + e];
+#pragma unroll
+      for (int d = 0; d < SD; ++d) {
+        mean[d] += (weight(k, d) / (wsum[d] + 1e-9f)) * z[((size_t)k * rows + r) * SD + d];
+#pragma unroll
+        for (int e = 0; e < SD; ++e) {
+          if (unimodal && K > 1) {
+            acc[d][e] += 1.0f / (L[d][e] + 1e-9f);
+          } else {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < SD; ++j) s = fmaf(L[d][j], L[e][j], s);
+            acc[d][e] += s;
+          }
+        }
+      }
+    }
+    if (unimodal) {
+      if (K > 1) {
+#pragma unroll
+        for (int d = 0; d < SD; ++d)
+#pragma unroll
+          for (int e = 0; e < SD; ++e) acc[d][e] += 1e-9f;
+        invert<SD>(acc, out);
+      } else {
+#pragma unroll
+        for (int d = 0; d < SD; ++d) {
+          mean[d] = z[(size_t)r * SD + d];
+#pragma unroll
+          for (int e = 0; e < SD; ++e) out[d][e] = acc[d][e];
+        }
+      }
+    } else {
+      // Cholesky factor (lower) of mult * sum_k L_k L_k^T; a non-positive pivot gives NaN like torch.linalg.cholesky raises
+#pragma unroll
+      for (int d = 0; d < SD; ++d)
+#pragma unroll
+        for (int e = 0; e < SD; ++e) {
+          acc[d][e] *= mult;
+          out[d][e] = 0.0f;
+        }
+#pragma unroll
+      for (int j = 0; j < SD; ++j) {
+        float s = acc[j][j];
+#pragma unroll
+        for (int q = 0; q < SD; ++q)
+          if (q < j) s -= out[j][q] * out[j][q];
+        const float piv = sqrtf(s);
+        out[j][j] = piv;
+#pragma unroll
+        for (int i = 0; i < SD; ++i) {
+          if (i > j) {
+            float t = acc[i][j];
+#pragma unroll
+            for (int q = 0; q < SD; ++q)
+              if (q < j) t -= out[i][q] * out[j][q];
+            out[i][j] = t / piv;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < SD; ++d) {
+      z_out[(size_t)r * SD + d] = mean[d];
+#pragma unroll
+      for (int e = 0; e < SD; ++e) mat_out[((size_t)r * SD + d) * SD + e] = out[d][e];
+    }
+  }
+}
+
+int launch_kf_fuse_measurements(int K, long long rows, int sd, const float* z, const float* tril, const float* w,
+                                float* z_out, float* mat_out, int unimodal, cudaStream_t stream) {
+  if (rows == 0) return MMF_OK;
+  long long blocks = (rows + 127) / 128;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  switch (sd) {
+    case 1: k_kf_fuse_measurements<1><<<(int)blocks, 128, 0, stream>>>(K, rows, z, tril, w, z_out, mat_out, unimodal); break;
+    case 2: k_kf_fuse_measurements<2><<<(int)blocks, 128, 0, stream>>>(K, rows, z, tril, w, z_out, mat_out, unimodal); break;
+    case 3: k_kf_fuse_measurements<3><<<(int)blocks, 128, 0, stream>>>(K, rows, z, tril, w, z_out, mat_out, unimodal); break;
+    case 4: k_kf_fuse_measurements<4><<<(int)blocks, 128, 0, stream>>>(K, rows, z, tril, w, z_out, mat_out, unimodal); break;
+    default: set_error("kf_fuse_measurements: state_dim %d unsupported", sd); return MMF_E_INVALID;
+  }
+  MMF_LAUNCH_CHECK("k_kf_fuse_measurements");
+  return MMF_OK;
+}
+
 }  // namespace mmf

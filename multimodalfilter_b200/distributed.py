@@ -92,7 +92,19 @@ class FlatGradients:
 
 
 class _NcclUniqueId(C.Structure):
-    _fields_ = [("internal", C.c_char * 128)]
+    _fields_ = [("internal", C.c_ubyte * 128)]  # raw bytes (a c_char array would read back truncated at the first NUL)
+
+
+def _loaded_nccl() -> str:
+    """Path of the NCCL library torch has mapped into this process (the bundled one), else the SONAME."""
+    try:
+        with open("/proc/self/maps") as maps:
+            for line in maps:
+                if "libnccl.so" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    return "libnccl.so.2"
 
 
 class StreamAllReduce:
@@ -112,17 +124,22 @@ class StreamAllReduce:
         if self.world == 1:
             return
         assert device.type == "cuda", "StreamAllReduce is the NCCL path; CPU tests use allreduce_gradients (gloo)"
-        self.lib = C.CDLL("libnccl.so.2")
+        self.lib = C.CDLL(_loaded_nccl())
         self.lib.ncclGetErrorString.restype = C.c_char_p
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _NcclUniqueId, C.c_int]
+        self.lib.ncclAllReduce.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         uid = _NcclUniqueId()
         if dist.get_rank() == 0:
             self._check(self.lib.ncclGetUniqueId(C.byref(uid)))
-        box = [bytes(uid.internal)] if dist.get_rank() == 0 else [None]
-        dist.broadcast_object_list(box, src=0, device=device)
-        C.memmove(C.byref(uid), box[0], 128)
+        # the 128 id bytes travel as a tensor through the process group that already exists
+        wire = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=device)
+        dist.broadcast(wire, src=0)
+        raw = bytes(wire.cpu().tolist())
+        assert len(raw) == 128
+        C.memmove(C.byref(uid), raw, 128)
         comm = C.c_void_p()
         with torch.cuda.device(device):
-            self._check(self.lib.ncclCommInitRank(C.byref(comm), C.c_int(self.world), uid, C.c_int(dist.get_rank())))
+            self._check(self.lib.ncclCommInitRank(C.byref(comm), self.world, uid, dist.get_rank()))
         self.comm = comm
 
     def _check(self, rc):
@@ -136,9 +153,8 @@ class StreamAllReduce:
         assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()
         stream = torch.cuda.current_stream(flat.device).cuda_stream
         with torch.cuda.device(flat.device):
-            self._check(self.lib.ncclAllReduce(C.c_void_p(flat.data_ptr()), C.c_void_p(flat.data_ptr()),
-                                               C.c_size_t(flat.numel()), C.c_int(self.FLOAT32),
-                                               C.c_int(self.AVG if average else self.SUM), self.comm, C.c_void_p(stream)))
+            self._check(self.lib.ncclAllReduce(flat.data_ptr(), flat.data_ptr(), flat.numel(), self.FLOAT32,
+                                               self.AVG if average else self.SUM, self.comm, stream))
         return flat.numel()
 
     def close(self):

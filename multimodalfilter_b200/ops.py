@@ -521,6 +521,27 @@ def kf_fuse_crossmodal(mu, P, beta):
     return mean, cov
 
 
+def kf_fuse_measurements(z, r_tril, weights=None):
+    """R12: z (K,*,sd), r_tril (K,*,sd,sd), weights (K,*,sd) or None (unimodal) -> fused z (*,sd) and a lower factor
+    (crossmodal) / covariance (unimodal) (*,sd,sd)."""
+    lib = _lib.load()
+    K, sd = z.shape[0], z.shape[-1]
+    lead = z.shape[1:-1]
+    rows = int(math.prod(lead))
+    z, r_tril = _f32c(z), _f32c(r_tril)
+    if weights is not None:
+        weights = _f32c(weights)
+        assert weights.shape == z.shape
+    assert r_tril.shape == (K, *lead, sd, sd)
+    z_out = torch.empty((*lead, sd), device=z.device, dtype=torch.float32)
+    mat = torch.empty((*lead, sd, sd), device=z.device, dtype=torch.float32)
+    _lib.check(
+        PROFILE.run("kf_fuse_measurements", 1, lib.mmf_kf_fuse_measurements, K, rows, sd, _lib.ptr(z), _lib.ptr(r_tril),
+                    None if weights is None else _lib.ptr(weights), _lib.ptr(z_out), _lib.ptr(mat), _lib.stream_of(z))
+    )
+    return z_out, mat
+
+
 def kf_fuse_unimodal(mu, P):
     """R11: information-form fusion of K Gaussian posteriors."""
     lib = _lib.load()

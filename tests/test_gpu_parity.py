@@ -762,3 +762,32 @@ def test_row_mlp_programs_match_torch_modules(rows):
         ops.PROFILE.reset()
         for g_, r_ in zip(got, ref):
             assert_close(g_.cpu(), r_.cpu(), 2e-5, msg=name)
+
+
+@pytest.mark.parametrize("K,sd,rows", [(1, 3, 5), (2, 3, 1000), (3, 2, 257), (2, 1, 64)])
+def test_kf_fuse_measurements_matches_the_reference_expressions(K, sd, rows):
+    """R12 (mmf_kf_fuse_measurements) against the torch expressions of the reference's CrossmodalVirtualSensorModel /
+    UnimodalVirtualSensorModel.forward (ref: crossmodal/base_models/crossmodal_kf.py:337-354, unimodal_kf.py:96-115)."""
+    g = torch.Generator().manual_seed(71 + K + sd)
+    z = torch.randn(K, rows, sd, generator=g)
+    tril = torch.tril(torch.randn(K, rows, sd, sd, generator=g)) * 0.3
+    tril.diagonal(dim1=-2, dim2=-1).abs_().add_(0.2)
+    w = torch.rand(K, rows, sd, generator=g) + 0.05
+    # crossmodal
+    got_z, got_l = ops.kf_fuse_measurements(z.to(DEV), tril.to(DEV), w.to(DEV))
+    ref_z, ref_cov = M._measurement_level(z, tril, w)
+    assert_close(got_z.cpu(), ref_z, 1e-5, msg="crossmodal z")
+    assert_close(got_l.cpu(), torch.linalg.cholesky(ref_cov), 1e-5, msg="crossmodal factor")
+    # unimodal (the reference's arithmetic: elementwise reciprocal of the factors, float64 torch as the yardstick
+    # because the matrix handed to inverse() holds K * 1e9 above its diagonal)
+    got_z, got_c = ops.kf_fuse_measurements(z.to(DEV), tril.to(DEV), None)
+    covs = tril @ tril.transpose(-1, -2)
+    if K == 1:
+        ref_z, ref_c = z[0], covs[0]
+    else:
+        prec = 1.0 / (tril + 1e-9)
+        wd = torch.diagonal(prec, dim1=-2, dim2=-1)
+        ref_z = M.weighted_average(z, wd)
+        ref_c = torch.inverse((prec.sum(dim=0) + 1e-9).double()).float()
+    assert_close(got_z.cpu(), ref_z, 1e-5, msg="unimodal z")
+    assert_close(got_c.cpu(), ref_c, 1e-4, msg="unimodal covariance")
