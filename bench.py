@@ -652,11 +652,15 @@ def main():
     line = {
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else precision,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if precision == "fp32" or (is_pf and _lib.load().mmf_pf_forward_loop_persistent(N, Mp)) else precision,
         "data": "synthetic",
         "config": {"workload": cfg, "id": args.workload, "model": name, "trajectories_per_gpu": N, "particles": Mp,
                    "filter_steps_per_pass": T, "resample": args.resample_mode if is_pf else None,
                    "precision": precision,
+                   "recursion": ("one launch for all T steps (k_pf_loop_small, fp32 CUDA cores, a CTA per trajectory)"
+                                 if is_pf and _lib.load().mmf_pf_forward_loop_persistent(N, Mp) else
+                                 "mmf_pf_forward_loop: 1 + 2 T launches" if is_pf else "k_ekf_loop: one launch for all T steps"),
                    "l2": "working set per filter step (particle states + weights + noise, C3: 115 MB) exceeds nothing "
                          "cached across passes: inputs larger than L2 over a pass; no explicit flush"},
         "clocks": clocks,

@@ -154,12 +154,20 @@ int mmf_pf_predict_measure(const mmf_pf_model* model, int32_t N, int32_t M, cons
  *   est_out (T, N, sd): the state estimate of every step;
  *   workspaces (caller-owned): rowbias_ws (1+K, T*N, 64) floats, states_ws (N, M, sd), logw_ws (N, M),
  *   resample_ws of mmf_pf_resample_workspace_bytes(N, M) bytes (may be NULL when that is 0).
- * Launches: 1 (per-trajectory rows of all T steps) + 2 per step (per-particle chain, normalise/estimate/resample). */
+ * Launches: 1 (per-trajectory rows of all T steps) + 2 per step (per-particle chain, normalise/estimate/resample).
+ * Small problems (M <= 64 particles and N <= one CTA per SM; mmf_pf_forward_loop_persistent(N, M) == 1) run the T steps
+ * in ONE further launch instead: a CTA carries a trajectory through the whole sequence, particle set in shared memory
+ * (MMF_PREC_FP32: CUDA-core arithmetic, identical bits to the per-step fp32 kernels; MMF_PREC_BF16X3 / BF16: the layers
+ * on mma.sync with the same split bf16 operands as the per-step tcgen05 kernel).  Environment MMF_PF_LOOP_SMALL, read
+ * once when the library is loaded: 0 = never, 1 = whenever M <= 128. */
 int mmf_pf_forward_loop(const mmf_pf_model* model, int32_t T, int32_t N, int32_t M, float* states, float* logw,
                         const float* controls, const float* const* obs_feats, const float* modality_logw,
                         uint32_t enabled_mask, int32_t precision, const float* eps, int32_t estimation_method,
                         int32_t resample_mode, const double* uniforms, float* rowbias_ws, float* states_ws,
                         float* logw_ws, float* est_out, void* resample_ws, void* stream);
+
+/* 1 when mmf_pf_forward_loop runs this shape through the one-launch whole-sequence kernel, else 0. */
+int mmf_pf_forward_loop_persistent(int32_t N, int32_t M);
 
 /* Second half of R6, and R7 (A.3): per trajectory
  *   logw = logw_unnorm - logsumexp_m(logw_unnorm);  est = sum_m exp(logw) x  (or argmax particle)

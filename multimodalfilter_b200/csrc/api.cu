@@ -140,6 +140,9 @@ int mmf_pf_forward_loop(const mmf_pf_model* model, int32_t T, int32_t N, int32_t
   // the per-trajectory rows of ALL steps in one launch: they do not depend on the particles
   rc = launch_traj_rows(model, T * N, controls, obs_feats, rowbias_ws, stream);
   if (rc) return rc;
+  if (pf_loop_small_applies(N, M))  // small problem: the T steps in ONE launch, a CTA per trajectory (pf_loop_small.cu)
+    return launch_pf_loop_small(model, T, N, M, states, logw, rowbias_ws, modality_logw, enabled_mask, precision, eps,
+                                estimation_method, resample_mode, uniforms, states_ws, logw_ws, est_out, stream);
   const size_t NM = (size_t)N * M;
   float* cur = states;     // particle set entering the step
   float* moved = states_ws;  // particle set after the dynamics (and, without resampling, after the step)
@@ -170,6 +173,8 @@ int mmf_pf_forward_loop(const mmf_pf_model* model, int32_t T, int32_t N, int32_t
   if (cur != states) MMF_CUDA(cudaMemcpyAsync(states, cur, NM * sd * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   return MMF_OK;
 }
+
+int mmf_pf_forward_loop_persistent(int32_t N, int32_t M) { return pf_loop_small_applies(N, M) ? 1 : 0; }
 
 size_t mmf_pf_resample_workspace_bytes(int32_t N, int32_t M) {
   if (N <= 0 || M <= 0) return 0;

@@ -53,6 +53,10 @@ int launch_pf_init(int N, int M, int sd, const float* mean, const float* cov, co
 int launch_normalize_resample(const ResampleParams& P, void* workspace, cudaStream_t stream);
 size_t resample_workspace_bytes(int N, int M);
 int launch_ekf(const EkfParams& P, int sd, cudaStream_t stream);
+bool pf_loop_small_applies(int N, int M);
+int launch_pf_loop_small(const mmf_pf_model* model, int T, int N, int M, float* states, float* logw, const float* rowbias,
+                         const float* modw, uint32_t enabled, int precision, const float* eps, int estimation, int mode,
+                         const double* uniforms, float* states_ws, float* logw_ws, float* est_out, cudaStream_t stream);
 int launch_kf_fuse_measurements(int K, long long rows, int sd, const float* z, const float* tril, const float* w,
                                 float* z_out, float* mat_out, int unimodal, cudaStream_t stream);
 int launch_kf_fuse(int K, long long rows, int sd, const float* mu, const float* Pk, const float* beta,

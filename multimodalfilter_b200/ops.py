@@ -352,7 +352,8 @@ def pf_predict_measure(model_struct, states, eps, rowbias, logw, modality_logw, 
 
 def pf_forward_loop(model_struct, states, logw, controls, feats, modality_logw, enabled_mask, eps, *, precision,
                     estimation, mode, uniforms):
-    """R1: the whole T-step recursion in one C call (1 + 2 T kernel launches).  states (N,M,sd) and logw (N,M) are
+    """R1: the whole T-step recursion in one C call (1 + 2 T kernel launches; small problems -- M <= 128, N up to two CTAs
+    per SM -- 2 launches: the per-trajectory rows and the one-launch whole-sequence kernel, fp32 arithmetic).  states (N,M,sd) and logw (N,M) are
     UPDATED IN PLACE to the particle set after the last step; controls (T,N,cd), feats: K tensors (T,N,F_k) or None,
     modality_logw (T,N,K)|None, eps (T,N*M,sd), uniforms float64 (T,N,M) | (T,N) | None.  Returns estimates (T,N,sd)."""
     lib = _lib.load()
@@ -383,7 +384,7 @@ def pf_forward_loop(model_struct, states, logw, controls, feats, modality_logw, 
         _lib.ptr(f)
     _lib.check(
         PROFILE.run(
-            "pf_forward_loop", 1 + 2 * T, lib.mmf_pf_forward_loop, C.byref(model_struct), T, N, M, _lib.ptr(states),
+            "pf_forward_loop", 2 if lib.mmf_pf_forward_loop_persistent(N, M) else 1 + 2 * T, lib.mmf_pf_forward_loop, C.byref(model_struct), T, N, M, _lib.ptr(states),
             _lib.ptr(logw), _lib.ptr(controls), arr, _lib.ptr(modality_logw), enabled_mask, precision, _lib.ptr(eps),
             estimation, mode, _lib.ptr(uniforms), _lib.ptr(rowbias), _lib.ptr(states_ws), _lib.ptr(logw_ws), _lib.ptr(est),
             _lib.ptr(ws), _lib.stream_of(states),

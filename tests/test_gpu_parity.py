@@ -791,3 +791,75 @@ def test_kf_fuse_measurements_matches_the_reference_expressions(K, sd, rows):
         ref_c = torch.inverse((prec.sum(dim=0) + 1e-9).double()).float()
     assert_close(got_z.cpu(), ref_z, 1e-5, msg="unimodal z")
     assert_close(got_c.cpu(), ref_c, 1e-4, msg="unimodal covariance")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name,M_,mode,estimation", [
+    ("PushCrossmodalParticleFilter", 30, "multinomial", "weighted_average"),
+    ("PushCrossmodalParticleFilter", 30, "systematic", "weighted_average"),
+    ("PushCrossmodalParticleFilter", 30, None, "weighted_average"),       # training-style: no resampling
+    ("PushUnimodalParticleFilter", 57, "multinomial", "argmax"),          # two particle chunks, ragged
+    ("DoorCrossmodalParticleFilter", 128, "multinomial", "weighted_average"),  # four chunks, state_dim 3
+    ("PushParticleFilter", 30, "multinomial_fast", "weighted_average"),
+])
+def test_one_launch_forward_loop_matches_the_per_step_kernels(name, M_, mode, estimation, precision):
+    """F2: small problems run all T steps in ONE launch (k_pf_loop_small, a CTA per trajectory).  Its chain arithmetic is
+    that of the fp32 per-step kernel (k_particle_chain_ffma) in the same order and its resampling IS nr_trajectory, so
+    against the per-step path at precision fp32 on the same draws everything agrees bit for bit in the strict modes:
+    estimates of every step, the final particle set, the final log-weights.  (The FAST modes' per-step path uses a
+    different kernel with its own logits: agreement to rounding there.)  At precision bf16x3 / bf16 the one-launch kernel
+    runs the layers on mma.sync with the same split bf16 operands as the tcgen05 per-step kernel: same products, another
+    summation order, so agreement is to fp32 rounding (bf16: to the single-pass grade) with the odd resampling tie."""
+    sd = 3 if name.startswith("Door") else 2
+    N, T = 5, 7
+    resample = mode is not None
+    init, eps, us = draw_noise(T, N, M_, sd, seed=81, systematic=bool(mode and mode.startswith("systematic")))
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=82)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd).to(DEV).contiguous()
+    o = {k: v[1:].to(DEV) for k, v in obs.items()}
+    lib = _lib.load()
+    if lib.mmf_pf_forward_loop_persistent(N, M_) != 1:
+        assert M_ > 64 and lib.mmf_pf_forward_loop_persistent(N, 64) == 1 and lib.mmf_pf_forward_loop_persistent(N, 129) == 0
+        pytest.skip("M > 64 takes the one-launch kernel only under MMF_PF_LOOP_SMALL=1 (tools/gpu scripts run that too)")
+    outs = []
+    for whole in (True, False):
+        p = fill_parameters(_product(name)(), seed=83).to(DEV).eval()
+        p.num_particles = M_
+        p.precision = precision
+        p.estimation_method = estimation
+        p.resample = resample
+        if resample:
+            p.resample_mode = mode
+        p.whole_loop = whole
+        p.noise = ReplayNoise(init_eps=init, process_eps=list(eps), uniforms=list(us))
+        ops.PROFILE.reset(enabled=True)
+        with torch.no_grad():
+            p.initialize_beliefs(mean=states[0].to(DEV), covariance=cov)
+            est = p.forward_loop(observations=o, controls=controls[1:].to(DEV))
+        kernels = ops.PROFILE.collect()["kernels"]
+        ops.PROFILE.reset()
+        assert ("pf_forward_loop" in kernels) == whole, sorted(kernels)
+        outs.append((est.clone(), p.particle_states.clone(), p.particle_log_weights.clone()))
+    torch.cuda.synchronize()
+    (e1, s1, l1), (e0, s0, l0) = outs
+    assert torch.isfinite(e1).all()
+    if precision != "fp32":
+        tol = 2e-5 if precision == "bf16x3" else 3e-2
+        scale = float(s0.abs().amax().clamp_min(1.0))
+        differing = ((s1 - s0).abs().amax(dim=-1) > 10 * tol * scale).float().mean() if mode is not None else 0.0
+        if estimation == "argmax" or precision == "bf16":  # a near-tie of two weights / a different draw moves an estimate
+            close = ((e1 - e0).abs().amax(dim=-1) <= tol * e0.abs().amax().clamp_min(1.0)).float().mean()
+            assert close > 0.9, f"only {float(close):.2f} of the estimates agree"
+        else:
+            assert_close(e1.cpu(), e0.cpu(), tol, msg="estimates")
+            assert differing < 0.02, "more than a few resampling ties differ"
+            if mode is None:
+                assert_close(s1.cpu(), s0.cpu(), tol, msg="final particles")
+                assert_close(l1.cpu(), l0.cpu(), tol, msg="final log-weights")
+    elif mode == "multinomial_fast":
+        assert_close(e1.cpu(), e0.cpu(), 1e-5, msg="estimates")
+        assert (s1 != s0).any(dim=-1).float().mean() < 0.02, "more than a few resampling ties differ"
+    else:
+        assert torch.equal(e1, e0), f"estimates differ: max |d| = {float((e1 - e0).abs().max()):.3e}"
+        assert torch.equal(s1, s0), "final particle states differ"
+        assert torch.equal(l1, l0), "final log-weights differ"
