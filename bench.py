@@ -66,12 +66,15 @@ def measured_peaks():
 
 def ncu_traffic(capture):
     """dram read + write bytes per launch of a kernel from the committed ncu --set full capture
-    (profiles/r01_ncu_metrics.json, written by tools/gpu_round.sh + the extraction step), or None."""
-    path = os.path.join(REPO, "profiles", "r01_ncu_metrics.json")
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        d = json.load(f).get(capture)
+    (profiles/r0N_ncu_metrics.json, written by tools/ncu_extract.py from the .ncu-rep files), or None."""
+    d = None
+    for rnd in ("r02", "r01"):  # the newest committed capture of this kernel
+        path = os.path.join(REPO, "profiles", f"{rnd}_ncu_metrics.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                d = json.load(f).get(capture)
+            if d:
+                break
     if not d or "dram_read" not in d or "dram_write" not in d:
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -653,12 +656,13 @@ def main():
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if precision == "fp32" or (is_pf and _lib.load().mmf_pf_forward_loop_persistent(N, Mp)) else precision,
+        "dtype": "f32" if precision == "fp32" else precision,
         "data": "synthetic",
         "config": {"workload": cfg, "id": args.workload, "model": name, "trajectories_per_gpu": N, "particles": Mp,
                    "filter_steps_per_pass": T, "resample": args.resample_mode if is_pf else None,
                    "precision": precision,
-                   "recursion": ("one launch for all T steps (k_pf_loop_small, fp32 CUDA cores, a CTA per trajectory)"
+                   "recursion": ("one launch for all T steps (k_pf_loop_small: a CTA per trajectory, particle set in shared memory, "
+                                 "layers on mma.sync with split bf16 operands; fp32 CUDA cores at precision fp32)"
                                  if is_pf and _lib.load().mmf_pf_forward_loop_persistent(N, Mp) else
                                  "mmf_pf_forward_loop: 1 + 2 T launches" if is_pf else "k_ekf_loop: one launch for all T steps"),
                    "l2": "working set per filter step (particle states + weights + noise, C3: 115 MB) exceeds nothing "
@@ -691,7 +695,7 @@ def main():
             line["roofline"] = {
                 "kernel": "k_particle_chain (mmf_pf_predict_measure)", "bound": "tensor", "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": ncu_traffic("prof_chain_tc") if args.workload == "c3" else None, "traffic_unit": "dram bytes per launch (ncu --set full, C3 step)",
+                "traffic": ncu_traffic("prof_chain_ws") if args.workload == "c3" and precision == "bf16x3" else None, "traffic_unit": "dram bytes per launch (ncu --set full, C3 step)",
                 "peak_source": f"{peaks['source']} bf16 sustained", "avg_launch_ms": k["avg_ms"],
                 "share_of_step": k["avg_ms"] * T / ms_resident,
                 "timed_in": "a pass that launches the kernels step by step (CUDA events per launch); value / ms_per_step "

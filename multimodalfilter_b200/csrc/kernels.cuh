@@ -18,6 +18,7 @@ struct ResampleParams {
   float* logw_norm_out;
   float* logits_out;
   long long* idx_out;
+  int prefetch = 0;  // k_resample_fast: request the trajectory's particles / uniforms from HBM up front
 };
 
 constexpr int EKF_MAX_FILTERS = 4;
