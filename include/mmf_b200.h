@@ -305,6 +305,19 @@ int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, int32_t sd, co
                               const float* x, const float* d_ll, float* dW_out, float* db_out, float* g_in_out,
                               float* g_out_out, void* workspace, void* stream);
 
+/* R5 + R6 of the BPTT step (no resampling, particle states without gradient) as one forward and one backward kernel:
+ *   fused = logsumexp_k(ll[k] + modality_logw[n,k]) over the enabled heads   (ref: crossmodal/base_models/crossmodal_pf.py:132-139)
+ *   logw_out = (logw_in + fused) - logsumexp_m(logw_in + fused);  est_out = sum_m exp(logw_out) states[n,m,:]   (A.3)
+ * ll (K,N,M) planes as mmf_pf_heads_forward_train writes them, modality_logw (N,K) or NULL, logw_in (N,M), states (N,M,sd).
+ * _bwd: given d_est (N,sd) and d_logw (N,M) (either may be NULL = zero) writes d_ll (K,N,M) (zeros for disabled heads),
+ * d_modality_logw (N,K) (may be NULL) and d_logw_in (N,M).  Nothing is saved between the calls: _bwd recomputes. */
+int mmf_pf_reweight_train_fwd(int32_t N, int32_t M, int32_t K, int32_t sd, uint32_t enabled_mask, const float* ll,
+                              const float* modality_logw, const float* logw_in, const float* states, float* logw_out,
+                              float* est_out, void* stream);
+int mmf_pf_reweight_train_bwd(int32_t N, int32_t M, int32_t K, int32_t sd, uint32_t enabled_mask, const float* ll,
+                              const float* modality_logw, const float* logw_in, const float* states, const float* d_est,
+                              const float* d_logw, float* d_ll, float* d_modality_logw, float* d_logw_in, void* stream);
+
 /* Per-trajectory MLP stacks (observation encoders of positions / sensors, crossmodal weight models, virtual-sensor heads:
  * ref: crossmodal/push_models/layers.py:107-136, crossmodal/push_models/crossmodal_pf.py:72-104,
  * crossmodal/door_models/crossmodal_kf.py:134-167, crossmodal/door_models/kf.py:81-126) as ONE launch: the host

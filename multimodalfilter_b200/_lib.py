@@ -129,6 +129,8 @@ PROTOTYPES = {
     "mmf_enc_trunk": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mmf_enc_stem": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "mmf_enc_conv3x3": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "mmf_pf_reweight_train_fwd": (C.c_int, [_i32, _i32, _i32, _i32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmf_pf_reweight_train_bwd": (C.c_int, [_i32, _i32, _i32, _i32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmf_row_mlp": (
         C.c_int,
         [C.c_int64, C.POINTER(MlpOp), _i32, _vp, C.POINTER(_vp), C.POINTER(_i32), C.POINTER(_i32), _i32, C.POINTER(_vp),

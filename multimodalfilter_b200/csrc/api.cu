@@ -361,6 +361,30 @@ int mmf_pf_heads_weight_grads(int32_t K, int32_t L, int64_t rows, int32_t sd, co
                          (cudaStream_t)stream);
 }
 
+int mmf_pf_reweight_train_fwd(int32_t N, int32_t M, int32_t K, int32_t sd, uint32_t enabled_mask, const float* ll,
+                              const float* modality_logw, const float* logw_in, const float* states, float* logw_out,
+                              float* est_out, void* stream) {
+  MMF_REQUIRE(N >= 0 && M >= 1 && K >= 1 && K <= MMF_MAX_HEADS && sd >= 1 && sd <= MMF_MAX_SD,
+              "reweight_train: bad shape N=%d M=%d K=%d sd=%d", N, M, K, sd);
+  MMF_REQUIRE((enabled_mask & ((1u << K) - 1u)) != 0, "reweight_train: no head enabled (mask 0x%x)", enabled_mask);
+  MMF_REQUIRE(N == 0 || (ll && logw_in && states && logw_out && est_out), "reweight_train: NULL buffer");
+  return launch_reweight_train(N, M, K, sd, enabled_mask & ((1u << K) - 1u), ll, modality_logw, logw_in, states, logw_out,
+                               est_out, nullptr, nullptr, nullptr, nullptr, nullptr, false, (cudaStream_t)stream);
+}
+
+int mmf_pf_reweight_train_bwd(int32_t N, int32_t M, int32_t K, int32_t sd, uint32_t enabled_mask, const float* ll,
+                              const float* modality_logw, const float* logw_in, const float* states, const float* d_est,
+                              const float* d_logw, float* d_ll, float* d_modality_logw, float* d_logw_in, void* stream) {
+  MMF_REQUIRE(N >= 0 && M >= 1 && K >= 1 && K <= MMF_MAX_HEADS && sd >= 1 && sd <= MMF_MAX_SD,
+              "reweight_train: bad shape N=%d M=%d K=%d sd=%d", N, M, K, sd);
+  MMF_REQUIRE((enabled_mask & ((1u << K) - 1u)) != 0, "reweight_train: no head enabled (mask 0x%x)", enabled_mask);
+  MMF_REQUIRE(N == 0 || (ll && logw_in && states && d_ll && d_logw_in), "reweight_train: NULL buffer");
+  MMF_REQUIRE((modality_logw == nullptr) == (d_modality_logw == nullptr) || d_modality_logw == nullptr,
+              "reweight_train: d_modality_logw given without modality_logw");
+  return launch_reweight_train(N, M, K, sd, enabled_mask & ((1u << K) - 1u), ll, modality_logw, logw_in, states, nullptr,
+                               nullptr, d_est, d_logw, d_ll, d_modality_logw, d_logw_in, true, (cudaStream_t)stream);
+}
+
 int mmf_row_mlp(int64_t rows, const mmf_mlp_op* ops, int32_t n_ops, const float* weights, const float* const* inputs,
                 const int32_t* in_dims, const int32_t* in_slots, int32_t n_inputs, float* const* outputs,
                 const int32_t* out_dims, const int32_t* out_slots, int32_t n_outputs, int32_t scratch_floats,

@@ -54,6 +54,9 @@ int launch_pf_init(int N, int M, int sd, const float* mean, const float* cov, co
 int launch_normalize_resample(const ResampleParams& P, void* workspace, cudaStream_t stream);
 size_t resample_workspace_bytes(int N, int M);
 int launch_ekf(const EkfParams& P, int sd, cudaStream_t stream);
+int launch_reweight_train(int N, int M, int K, int sd, uint32_t enabled, const float* ll, const float* w, const float* logw_in,
+                          const float* states, float* logw_out, float* est_out, const float* d_est, const float* d_logw,
+                          float* d_ll, float* d_w, float* d_logw_in, bool backward, cudaStream_t stream);
 bool pf_loop_small_applies(int N, int M);
 int launch_pf_loop_small(const mmf_pf_model* model, int T, int N, int M, float* states, float* logw, const float* rowbias,
                          const float* modw, uint32_t enabled, int precision, const float* eps, int estimation, int mode,

@@ -522,6 +522,39 @@ def kf_fuse_crossmodal(mu, P, beta):
     return mean, cov
 
 
+def pf_reweight_train_fwd(ll, modality_logw, logw_in, states, enabled_mask):
+    """R5 + R6 of the BPTT step: ll (K,N,M), modality_logw (N,K)|None, logw_in (N,M), states (N,M,sd) ->
+    normalised log-weights (N,M), weighted-average estimate (N,sd)."""
+    lib = _lib.load()
+    K, N, M = ll.shape
+    sd = states.shape[-1]
+    ll, logw_in, states = _f32c(ll), _f32c(logw_in), _f32c(states)
+    modality_logw = None if modality_logw is None else _f32c(modality_logw)
+    assert logw_in.shape == (N, M) and states.shape == (N, M, sd) and (modality_logw is None or modality_logw.shape == (N, K))
+    logw = torch.empty((N, M), device=ll.device, dtype=torch.float32)
+    est = torch.empty((N, sd), device=ll.device, dtype=torch.float32)
+    _lib.check(PROFILE.run("pf_reweight_train_fwd", 1, lib.mmf_pf_reweight_train_fwd, N, M, K, sd, enabled_mask, _lib.ptr(ll),
+                           _lib.ptr(modality_logw), _lib.ptr(logw_in), _lib.ptr(states), _lib.ptr(logw), _lib.ptr(est),
+                           _lib.stream_of(ll)))
+    return logw, est
+
+
+def pf_reweight_train_bwd(ll, modality_logw, logw_in, states, enabled_mask, d_est, d_logw):
+    """Reverse mode of ``pf_reweight_train_fwd``: -> d_ll (K,N,M), d_modality_logw (N,K)|None, d_logw_in (N,M)."""
+    lib = _lib.load()
+    K, N, M = ll.shape
+    sd = states.shape[-1]
+    d_est = None if d_est is None else _f32c(d_est)
+    d_logw = None if d_logw is None else _f32c(d_logw)
+    d_ll = torch.empty((K, N, M), device=ll.device, dtype=torch.float32)
+    d_w = None if modality_logw is None else torch.empty((N, K), device=ll.device, dtype=torch.float32)
+    d_in = torch.empty((N, M), device=ll.device, dtype=torch.float32)
+    _lib.check(PROFILE.run("pf_reweight_train_bwd", 1, lib.mmf_pf_reweight_train_bwd, N, M, K, sd, enabled_mask, _lib.ptr(ll),
+                           _lib.ptr(modality_logw), _lib.ptr(logw_in), _lib.ptr(states), _lib.ptr(d_est), _lib.ptr(d_logw),
+                           _lib.ptr(d_ll), _lib.ptr(d_w), _lib.ptr(d_in), _lib.stream_of(ll)))
+    return d_ll, d_w, d_in
+
+
 def kf_fuse_measurements(z, r_tril, weights=None):
     """R12: z (K,*,sd), r_tril (K,*,sd,sd), weights (K,*,sd) or None (unimodal) -> fused z (*,sd) and a lower factor
     (crossmodal) / covariance (unimodal) (*,sd,sd)."""

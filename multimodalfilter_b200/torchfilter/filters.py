@@ -85,6 +85,7 @@ class ParticleFilter(Filter):
         # same shapes captures the whole T-step recursion in a CUDA graph and later calls replay it
         self.graph_max_particles = 1 << 16  # N * M up to which forward_loop is graph-captured; 0 disables
         self.whole_loop = True  # forward_loop through mmf_pf_forward_loop (one C call); False: one kernel sequence per step
+        self.fused_reweight = True  # training step: fusion / normalise / estimate and their backward as two kernels
 
     # ---- plan management -------------------------------------------------------------------------
     def fused_plan(self):
@@ -182,12 +183,17 @@ class ParticleFilter(Filter):
         eps = self._process_eps(N * M, sd, states)
         moved, ll = training.FusedHeads.apply(plan, states, eps, dyn_row, torch.stack(rows), plan.enabled_mask(),
                                              ops.PRECISIONS[self.precision], *params)
+        modw = plan.modality_log_weights(observations) if hoisted is None else hoisted[1]
+        if self.estimation_method == "weighted_average" and self.fused_reweight:
+            # fusion over the enabled heads + reweight + normalise + estimate: one kernel, and one more for its backward
+            logw_n, estimate = training.Reweight.apply(ll, modw, logw, moved, plan.enabled_mask())
+            self.particle_states, self.particle_log_weights = moved, logw_n
+            return estimate
         # select the enabled heads by slicing: indexing with a Python list would build the index tensor on the host and
         # copy it over (a synchronising H2D copy per step, and not capturable in a CUDA graph)
         on_idx = [k for k, on in enumerate(enabled) if on]
         all_on = len(on_idx) == len(enabled)
         ll = (ll if all_on else torch.stack([ll[k] for k in on_idx])).permute(1, 2, 0)  # (N, M, K_enabled)
-        modw = plan.modality_log_weights(observations) if hoisted is None else hoisted[1]
         if modw is not None:
             mw = modw if all_on else torch.stack([modw[:, k] for k in on_idx], dim=1)
             ll = ll + mw[:, None, :]

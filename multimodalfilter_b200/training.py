@@ -108,6 +108,32 @@ class FusedHeads(torch.autograd.Function):
         return (None, None, None, None, d_rows, None, None, *grads)
 
 
+class Reweight(torch.autograd.Function):
+    """(ll[K, N, M], modality log-weights (N, K) | None, logw_in (N, M), moved states) -> (normalised logw (N, M), estimate
+    (N, sd)): fusion over the enabled heads, reweighting, normalisation and the weighted-average estimate of A.3 in one
+    kernel, and their reverse mode in one more (``mmf_pf_reweight_train_fwd / _bwd``; the backward recomputes instead of
+    saving intermediates).  The particle states carry no gradient (frozen dynamics)."""
+
+    @staticmethod
+    def forward(ctx, ll, modw, logw_in, states, enabled_mask):
+        ll, logw_in, states = ll.contiguous(), logw_in.contiguous(), states.detach().contiguous()
+        modw = None if modw is None else modw.contiguous()
+        logw, est = ops.pf_reweight_train_fwd(ll.detach(), None if modw is None else modw.detach(), logw_in.detach(), states,
+                                              enabled_mask)
+        ctx.mask = enabled_mask
+        ctx.has_modw = modw is not None
+        ctx.save_for_backward(ll, logw_in, states, *([modw] if modw is not None else []))
+        ctx.set_materialize_grads(False)
+        return logw, est
+
+    @staticmethod
+    def backward(ctx, d_logw, d_est):
+        ll, logw_in, states, *rest = ctx.saved_tensors
+        modw = rest[0] if ctx.has_modw else None
+        d_ll, d_w, d_in = ops.pf_reweight_train_bwd(ll, modw, logw_in, states, ctx.mask, d_est, d_logw)
+        return d_ll, d_w, d_in, None, None
+
+
 def fused_train_applicable(filt, plan, resample: bool) -> bool:
     """The fused training step covers exactly the reference's setting: no resampling, frozen dynamics,
     particle states without gradient, tensor-core precision."""

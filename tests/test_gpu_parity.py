@@ -863,3 +863,54 @@ def test_one_launch_forward_loop_matches_the_per_step_kernels(name, M_, mode, es
         assert torch.equal(e1, e0), f"estimates differ: max |d| = {float((e1 - e0).abs().max()):.3e}"
         assert torch.equal(s1, s0), "final particle states differ"
         assert torch.equal(l1, l0), "final log-weights differ"
+
+
+@pytest.mark.parametrize("K,mask,with_w,M_", [(2, 0b11, True, 30), (2, 0b10, True, 30), (3, 0b101, False, 77), (1, 0b1, False, 1000)])
+def test_reweight_train_kernels_match_torch_autograd(K, mask, with_w, M_):
+    """mmf_pf_reweight_train_fwd / _bwd (training.Reweight: fusion over the enabled heads, reweight, normalise, estimate and
+    their reverse mode) against the torch expressions of the training step and torch autograd, including a blacked-out
+    modality (-inf weight) on some trajectories."""
+    from multimodalfilter_b200 import training
+
+    N, sd = 37, 2
+    g = torch.Generator().manual_seed(91 + K + M_)
+    ll = torch.randn(K, N, M_, generator=g) * 3.0
+    modw = torch.randn(N, K, generator=g) if with_w else None
+    on = [k for k in range(K) if (mask >> k) & 1]
+    if with_w and len(on) > 1:
+        modw[::5, on[0]] = -float("inf")  # quirk Q3: image blackout
+    logw_in = torch.log_softmax(torch.randn(N, M_, generator=g), dim=1)
+    states = torch.randn(N, M_, sd, generator=g)
+    d_est = torch.randn(N, sd, generator=g)
+    d_logw = torch.randn(N, M_, generator=g) * 0.1
+
+    def run(fn, dev):
+        a = ll.to(dev).double().requires_grad_() if dev == "cpu" else ll.to(dev).requires_grad_()
+        w = None if modw is None else (modw.to(dev).double() if dev == "cpu" else modw.to(dev)).requires_grad_()
+        li = (logw_in.to(dev).double() if dev == "cpu" else logw_in.to(dev)).requires_grad_()
+        x = states.to(dev).double() if dev == "cpu" else states.to(dev)
+        logw, est = fn(a, w, li, x)
+        loss = (est * d_est.to(est)).sum() + (logw * d_logw.to(logw)).sum()
+        loss.backward()
+        return logw.detach().cpu(), est.detach().cpu(), a.grad.cpu(), None if w is None else w.grad.cpu(), li.grad.cpu()
+
+    def torch_expr(a, w, li, x):  # the expressions of ParticleFilter._step_fused_train's torch path, in float64
+        v = torch.stack([a[k] for k in on], dim=2)
+        if w is not None:
+            v = v + torch.stack([w[:, k] for k in on], dim=1)[:, None, :]
+        u = li + torch.logsumexp(v, dim=2)
+        ln = u - torch.logsumexp(u, dim=1, keepdim=True)
+        return ln, torch.sum(torch.exp(ln)[:, :, None] * x, dim=1)
+
+    ref = run(torch_expr, "cpu")
+    got = run(lambda a, w, li, x: training.Reweight.apply(a, w, li, x, mask), DEV)
+    names = ["logw", "estimate", "d_ll", "d_modality_logw", "d_logw_in"]
+    for name, r, q in zip(names, ref, got):
+        if r is None:
+            assert q is None
+            continue
+        r = torch.nan_to_num(r.float(), nan=0.0)  # torch autograd: 0 * inf = nan on the blacked-out column; the kernel gives 0
+        if name == "d_ll":
+            off = [k for k in range(K) if k not in on]
+            assert all(float(q[k].abs().max()) == 0.0 for k in off), "gradient leaked into a disabled head"
+        assert_close(q, r, 2e-5, atol=1e-6, msg=name)
