@@ -298,11 +298,11 @@ def run_c4(ctx, steps, warmup, precision):
     def forward_backward():
         grads.zero()
         filt.initialize_beliefs(mean=mean0, covariance=cov)
-        ests = []
-        for t in range(T):
-            modw = wm.fusion_layers(wm_feats[t])
-            ests.append(filt.forward(observations=None, controls=controls[t], _hoisted=([feats[0][t], feats[1][t]], modw)))
-        loss = torch.mean((torch.stack(ests) - targets) ** 2)
+        # what forward_loop does in train mode: the per-trajectory pieces (weight-model fusion layers, the heads'
+        # observation rows, the dynamics rows) once over all T * N rows, then the per-particle kernels step by step
+        modw = wm.fusion_layers(wm_feats.reshape(T * N, -1)).reshape(T, N, -1)
+        ests = filt.forward_loop_train_hoisted(feats, modw, controls)
+        loss = torch.mean((ests - targets) ** 2)
         loss.backward()
         if in_graph:
             reduce_(grads.flat)  # ncclAllReduce (avg) on this stream

@@ -162,28 +162,45 @@ class ParticleFilter(Filter):
             return self._step_fused_train(plan, observations, controls, _hoisted)
         return self._step_generic(observations, controls, resample, mode, grad)
 
-    def _step_fused_train(self, plan, observations, controls, hoisted=None):
-        """BPTT step (train mode: no resampling; dynamics frozen): kernels for the per-particle work, torch
-        ops with autograd for the (N, M)-sized fusion / normalisation / estimate and the per-trajectory modules."""
+    def _head_rows(self, plan, observations, feats, rows_n):
+        """(K, rows_n, 64): the observation half of every enabled head's first shared Linear (autograd on)."""
+        rows = []
+        for spec, on in zip(plan.heads, plan.enabled()):
+            if not on:
+                rows.append(self.particle_states.new_zeros((rows_n, fused.U)))
+                continue
+            mid = spec.shared[0]
+            f = spec.observation_features(observations) if feats is None else feats[len(rows)]
+            rows.append(torch.nn.functional.linear(f, mid.weight[:, : spec.feat_dim], mid.bias))
+        return torch.stack(rows)
+
+    def _step_fused_train(self, plan, observations, controls, hoisted=None, pre=None):
+        """BPTT step (train mode: no resampling; dynamics frozen): kernels for the per-particle work and for fusion /
+        normalisation / estimate, torch modules with autograd for the per-trajectory pieces.  ``pre`` = (dynamics row,
+        head rows (K, N, 64), modality log-weights) when ``forward_loop`` computed them for the whole sequence."""
         states, logw = self.particle_states, self.particle_log_weights
         N, M, sd = states.shape
         enabled = plan.enabled()
         plan.refresh(states.device, backward=True)
-        with torch.no_grad():
-            dyn_row = ops.pf_traj_rows(plan.struct, plan.K, controls, [None] * plan.K)[0]
-        rows, params = [], []
-        for spec, on in zip(plan.heads, enabled):
-            params += training.head_parameters(spec)
-            if not on:
-                rows.append(states.new_zeros((N, fused.U)))
-                continue
-            mid = spec.shared[0]
-            feats = spec.observation_features(observations) if hoisted is None else hoisted[0][len(rows)]
-            rows.append(torch.nn.functional.linear(feats, mid.weight[:, : spec.feat_dim], mid.bias))
+        params = [p for spec in plan.heads for p in training.head_parameters(spec)]
+        if pre is None:
+            with torch.no_grad():
+                dyn_row = ops.pf_traj_rows(plan.struct, plan.K, controls, [None] * plan.K)[0]
+            head_rows = self._head_rows(plan, observations, None if hoisted is None else hoisted[0], N)
+            modw = plan.modality_log_weights(observations) if hoisted is None else hoisted[1]
+        else:
+            dyn_row, head_rows, modw = pre
         eps = self._process_eps(N * M, sd, states)
-        moved, ll = training.FusedHeads.apply(plan, states, eps, dyn_row, torch.stack(rows), plan.enabled_mask(),
-                                             ops.PRECISIONS[self.precision], *params)
-        modw = plan.modality_log_weights(observations) if hoisted is None else hoisted[1]
+        # one gradient token per autograd graph: the head parameters' gradients of all steps of a sequence are summed as
+        # one flat tensor and distributed to the parameters once (training.HeadGradToken).  A carried log-weight without
+        # grad_fn marks the start of a new graph (initialize_beliefs, or a detach for truncated BPTT): new token.
+        tok = self.__dict__.get("_train_token")
+        if tok is None or tok[0] is not plan or logw.grad_fn is None or not torch.is_grad_enabled():
+            info = {"used": 0}
+            tok = (plan, training.HeadGradToken.apply(plan, info, *params), info)
+            self.__dict__["_train_token"] = tok
+        moved, ll = training.FusedHeads.apply(plan, states, eps, dyn_row, head_rows, plan.enabled_mask(),
+                                             ops.PRECISIONS[self.precision], tok[1], tok[2])
         if self.estimation_method == "weighted_average" and self.fused_reweight:
             # fusion over the enabled heads + reweight + normalise + estimate: one kernel, and one more for its backward
             logw_n, estimate = training.Reweight.apply(ll, modw, logw, moved, plan.enabled_mask())
@@ -280,9 +297,27 @@ class ParticleFilter(Filter):
             or not isinstance(controls, torch.Tensor)
             or not isinstance(observations, dict)
             or _has_hooks(self)
-            or _needs_grad(self, self.particle_states, self.particle_log_weights)
         ):
             return super().forward_loop(observations=observations, controls=controls)
+        if _needs_grad(self, self.particle_states, self.particle_log_weights):
+            resample, _ = self._modes()
+            T, N = controls.shape[:2]
+            if (not controls.is_cuda or not training.fused_train_applicable(self, plan, resample)
+                    or self.num_particles != self.particle_states.shape[1]
+                    or not all(isinstance(v, torch.Tensor) and v.is_cuda for v in observations.values())):
+                return super().forward_loop(observations=observations, controls=controls)
+            # training: encoders, weight model and the heads' observation rows once over all T * N rows, with autograd
+            flat = fused.flatten_time(observations, T, N)
+            feats = [spec.observation_features(flat) if on else None for spec, on in zip(plan.heads, plan.enabled())]
+            wm = getattr(plan.mm, "crossmodal_weight_model", None) if plan.composite else None
+            if wm is None:
+                modw = None
+            elif type(wm).__name__ in TIME_BATCHABLE or getattr(wm, "_mmf_time_batchable", False):
+                modw = plan.modality_log_weights(flat)
+            else:  # a user weight model may couple the rows of a batch: one call per step, as the reference does
+                obs = SliceWrapper(observations)
+                modw = torch.stack([plan.modality_log_weights(obs[t]) for t in range(T)])
+            return self.forward_loop_train_hoisted(feats, modw, controls)
         require_cuda(controls, "controls")
         T, N = controls.shape[:2]
         assert SliceWrapper(observations).shape[:2] == (T, N), "observations and controls disagree on (T, N)"
@@ -293,6 +328,26 @@ class ParticleFilter(Filter):
         if isinstance(observations, fused.StagedObservations):
             observations.ready(T * N)
         return self.forward_loop_hoisted(feats, modw, controls)
+
+    def forward_loop_train_hoisted(self, feats, modw, controls) -> torch.Tensor:
+        """BPTT over a sequence with everything that does not depend on the particles computed ONCE for all T steps
+        (training side): the observation halves of the heads' first shared Linear
+        (``feats``: K tensors (T, N, F_k) of observation features, gradients welcome), the dynamics rows of all steps
+        (one ``mmf_pf_traj_rows`` launch) and the modality log-weights ``modw`` (T, N, K) | None.  Per step only the
+        per-particle kernels (``FusedHeads``) and the reweight kernels (``Reweight``) remain.  Same numbers as T calls of
+        ``forward``."""
+        plan = self.fused_plan()
+        T, N = controls.shape[:2]
+        plan.refresh(controls.device, backward=True)
+        flat = [None if f is None else f.reshape(T * N, -1) for f in feats]
+        rows_all = self._head_rows(plan, None, flat, T * N).view(plan.K, T, N, fused.U).unbind(1)
+        with torch.no_grad():
+            dyn_rows = ops.pf_traj_rows(plan.struct, plan.K, controls.reshape(T * N, -1), [None] * plan.K)[0].view(T, N, fused.U)
+        modw_t = [None] * T if modw is None else modw.reshape(T, N, -1).unbind(0)
+        estimates = []
+        for t in range(T):
+            estimates.append(self._step_fused_train(plan, None, controls[t], pre=(dyn_rows[t], rows_all[t], modw_t[t])))
+        return torch.stack(estimates)
 
     def forward_loop_hoisted(self, feats, modw, controls) -> torch.Tensor:
         """The recursion proper, given the per-head observation features (T, N, F_k) and modality log-weights

@@ -36,9 +36,14 @@ def head_parameters(spec) -> List[torch.Tensor]:
     return ps
 
 
-def _grads_for_head(spec, dW, db, g_in, g_out, d_ll):
-    """dW (L, 64, 64), db (L+1, 64), g_in (64, sd), g_out (64,) from mmf_pf_heads_weight_grads; d_ll (P,).
-    Returns grads in head_parameters order and the index of the mid layer."""
+def mid_layer_index(spec) -> int:
+    return 2 * len(spec.state[1])
+
+
+def _grads_for_head(spec, dW, db, g_in, g_out, d_ll_sum):
+    """dW (L, 64, 64), db (L+1, 64), g_in (64, sd), g_out (64,) from mmf_pf_heads_weight_grads; d_ll_sum (1,) = the sum
+    of d ll over the particles (gradient of the output bias).  Returns grads in head_parameters order and the index of
+    the mid layer."""
     (in_lin, pre), (mid, post, out) = spec.state, spec.shared
     L = 2 * len(pre) + 1 + 2 * len(post)
     grads = [g_in, db[L]]
@@ -56,15 +61,60 @@ def _grads_for_head(spec, dW, db, g_in, g_out, d_ll):
         for _half in range(2):
             grads += [dW[layer], db[layer]]
             layer += 1
-    grads += [g_out[None, :], d_ll.sum().reshape(1)]
+    grads += [g_out[None, :], d_ll_sum.reshape(1)]
     return grads, mid_layer
 
 
-class FusedHeads(torch.autograd.Function):
-    """(states, eps, dynamics row, head rows, head parameters...) -> (moved, ll[K_enabled, N, M])."""
+class HeadGradToken(torch.autograd.Function):
+    """All head parameters of a plan -> ONE flat tensor whose only purpose is to carry gradients: ``FusedHeads`` takes the
+    token instead of the ~30 parameters per head and hands its backward the per-step parameter gradients as one flat
+    tensor [dW | db | g_in | g_out | sum d_ll] per head.  Over a T-step sequence autograd then sums T flat tensors (T - 1
+    adds) and this node distributes the total to the parameters ONCE, instead of 61 ``AccumulateGrad`` additions per
+    filter step (915 small kernels per C4 training step).  Heads that no step of the sequence enabled get ``None``."""
 
     @staticmethod
-    def forward(ctx, plan, states, eps, dyn_row, head_rows, enabled_mask, precision, *params):
+    def forward(ctx, plan, info, *params):
+        ctx.plan, ctx.info = plan, info
+        return params[0].new_zeros(token_size(plan))
+
+    @staticmethod
+    def backward(ctx, d_token):
+        plan, info = ctx.plan, ctx.info
+        per_head = token_size(plan) // plan.K
+        grads = []
+        for k, spec in enumerate(plan.heads):
+            n_params = len(head_parameters(spec))
+            if d_token is None or not (info["used"] >> k) & 1:
+                grads += [None] * n_params
+                continue
+            L, sd = _layers(spec), spec.sd
+            part = d_token[k * per_head:(k + 1) * per_head]
+            o = 0
+            dW = part[o:o + L * U * U].view(L, U, U); o += L * U * U
+            db = part[o:o + (L + 1) * U].view(L + 1, U); o += (L + 1) * U
+            g_in = part[o:o + U * sd].view(U, sd); o += U * sd
+            g_out = part[o:o + U]; o += U
+            g, _ = _grads_for_head(spec, dW, db, g_in, g_out, part[o:o + 1])
+            grads += g
+        return (None, None, *grads)
+
+
+def _layers(spec) -> int:
+    return 2 * len(spec.state[1]) + 1 + 2 * len(spec.shared[1])
+
+
+def token_size(plan) -> int:
+    spec = plan.heads[0]
+    L, sd = _layers(spec), spec.sd
+    return plan.K * (L * U * U + (L + 1) * U + U * sd + U + 1)
+
+
+class FusedHeads(torch.autograd.Function):
+    """(states, eps, dynamics row, head rows, gradient token of the head parameters) -> (moved, ll[K, N, M])."""
+
+    @staticmethod
+    def forward(ctx, plan, states, eps, dyn_row, head_rows, enabled_mask, precision, token, info):
+        info["used"] |= enabled_mask
         N, M, sd = states.shape
         dev = states.device
         plan.refresh(dev, backward=True)
@@ -95,17 +145,14 @@ class FusedHeads(torch.autograd.Function):
                     delta[k].zero_()
         moved_flat = moved.reshape(N * M, sd)
         dW, db, g_in, g_out = ops.pf_heads_weight_grads(act, delta, moved_flat, d_ll.reshape(plan.K, N * M))
-        d_rows = torch.zeros((plan.K, N, U), device=act.device, dtype=torch.float32)
-        grads = []
-        for k, spec in enumerate(plan.heads):
-            n_params = len(head_parameters(spec))
-            if not (mask >> k) & 1:
-                grads += [None] * n_params
-                continue
-            g, mid_layer = _grads_for_head(spec, dW[k], db[k], g_in[k], g_out[k], d_ll[k].reshape(-1))
-            grads += g
-            d_rows[k] = delta[k, mid_layer].view(U // 4, N, M, 4).sum(dim=2).permute(1, 0, 2).reshape(N, U)
-        return (None, None, None, None, d_rows, None, None, *grads)
+        K = plan.K
+        # per-trajectory row gradients: the mid layer's delta summed over the particles (chunk-major planes -> (N, 64))
+        mid_layer = mid_layer_index(plan.heads[0])
+        d_rows = delta[:, mid_layer].view(K, U // 4, N, M, 4).sum(dim=3).permute(0, 2, 1, 3).reshape(K, N, U)
+        # this step's parameter gradients as ONE flat tensor, per head [dW | db | g_in | g_out | sum d_ll] (HeadGradToken)
+        d_token = torch.cat([dW.reshape(K, -1), db.reshape(K, -1), g_in.reshape(K, -1), g_out.reshape(K, -1),
+                             d_ll.reshape(K, -1).sum(dim=1, keepdim=True)], dim=1).reshape(-1)
+        return (None, None, None, None, d_rows, None, None, d_token, None)
 
 
 class Reweight(torch.autograd.Function):

@@ -146,3 +146,56 @@ def test_train_e2e_runs_the_fused_bptt_step():
     assert all(p.grad is None for p in model.dynamics_model.parameters())
     assert any(p.grad is not None and p.grad.abs().sum() > 0 for n, p in model.named_parameters()
                if "observation_image_layers.0" in n), "the image-encoder CNN received no gradient"
+
+
+@pytest.mark.gpu
+def test_training_forward_loop_hoists_the_per_trajectory_pieces():
+    """forward_loop in train mode computes encoders / weight model / the heads' observation rows once over all T * N rows
+    and then runs the per-particle kernels step by step: loss and every parameter gradient must equal T calls of forward()
+    (same draws) to fp32 rounding, and parameters of the encoders must receive gradients on both routes."""
+    import torch
+    from multimodalfilter_b200 import ops
+    from multimodalfilter_b200.crossmodal import models as M
+    from multimodalfilter_b200.synthetic import fill_parameters, synthetic_trajectories
+    from util import ReplayNoise, assert_close, draw_noise
+
+    dev, sd, N, Mp, T = "cuda:0", 2, 12, 30, 6
+    init, eps, _ = draw_noise(T, N, Mp, sd, seed=51)
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=52)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd).to(dev).contiguous()
+    o = {k: v[1:].to(dev) for k, v in obs.items()}
+    c = controls[1:].to(dev)
+    target = states[1:].to(dev)
+    results = []
+    for hoisted in (False, True):
+        f = fill_parameters(M.PushCrossmodalParticleFilter(), seed=53).to(dev)
+        f.train()
+        for p in f.dynamics_model.parameters():
+            p.requires_grad_(False)  # the reference's end-to-end curricula freeze the dynamics
+        f.noise = ReplayNoise(init_eps=init, process_eps=list(eps), uniforms=[])
+        f.initialize_beliefs(mean=states[0].to(dev), covariance=cov)
+        ops.PROFILE.reset(enabled=True)
+        if hoisted:
+            est = f.forward_loop(observations=o, controls=c)
+        else:
+            est = torch.stack([f.forward(observations={k: v[t] for k, v in o.items()}, controls=c[t]) for t in range(T)])
+        loss = torch.mean((est - target) ** 2)
+        loss.backward()
+        kernels = ops.PROFILE.collect()["kernels"]
+        ops.PROFILE.reset()
+        assert kernels["pf_heads_forward_train"]["count"] == T and kernels["pf_reweight_train_bwd"]["count"] == T
+        assert kernels["pf_traj_rows"]["count"] == (1 if hoisted else T)
+        results.append((float(loss), {k: p.grad.detach().cpu().clone() for k, p in f.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = results
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    assert set(g0) == set(g1) and len(g0) > 80 and any("observation_image_layers" in k for k in g0)
+    # Same mathematics, different batching of the library GEMMs / cuDNN (12 rows per step vs 72 at once): the per-trajectory
+    # rows differ in the last bit, which flips the odd ReLU of the odd particle (an O(1) change of that particle's
+    # contribution, DESIGN.md section 9) and re-orders the CNN's heavily cancelling weight-gradient sums.  The check is
+    # therefore per tensor: direction and magnitude; a missing or doubled contribution would show up as O(1).
+    big = max(float(g.norm()) for g in g0.values())
+    for k in g0:
+        a, b = g1[k].double().reshape(-1), g0[k].double().reshape(-1)
+        rel = float((a - b).norm() / max(float(b.norm()), 1e-3 * big))
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30)) if float(b.norm()) > 1e-3 * big else 1.0
+        assert rel <= 2e-2 and cos >= 0.999, f"{k}: relative L2 {rel:.2e}, cosine {cos:.5f}"
