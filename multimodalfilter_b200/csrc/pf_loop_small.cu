@@ -56,6 +56,94 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Normalise / estimate / resample of ONE trajectory with M <= 32 particles, in registers: lane j owns particle j and draw j.
+// Same operations on the same values in the same order as nr_trajectory<32> (normalize_resample.cuh) for the cases it
+// covers -- hard resampling that keeps the particle count, modes NONE / MULTINOMIAL_STRICT / SYSTEMATIC_STRICT -- so the
+// outputs are identical bit for bit (tests/test_gpu_parity.py::test_one_launch_forward_loop_matches_the_per_step_kernels
+// compares against the per-step kernels, which run nr_trajectory).  What it sheds: the generic path's shared-memory
+// round trips, guide table and padded loops, ~4x the instructions at this size (ncu: a third of a C1 step).
+//   * sum exp / estimate: every `for (i = lane; i < M; i += 32)` loop of the generic code has at most one iteration here;
+//   * strict CDF: c_j = fl(c_{j-1} + e_j), the sequential sum, formed redundantly by all lanes from shuffled e_k;
+//   * inverse CDF: idx = #{k : c_k < c*} with c* = cdf_threshold(total, u), the exact form of the pinned predicate.
+// All pointers of R already address this trajectory (the generic function is called with n = 0 the same way).
+__device__ __forceinline__ bool nr_small_applies(const ResampleParams& R) {
+  return R.M <= 32 && R.M_out == R.M && !(R.alpha < 1.0f) && R.logits_in == nullptr && R.logw_norm_out == nullptr &&
+         R.logits_out == nullptr && R.idx_out == nullptr &&
+         (R.mode == MMF_RESAMPLE_NONE || R.mode == MMF_RESAMPLE_MULTINOMIAL_STRICT || R.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT);
+}
+
+__device__ __forceinline__ void nr_small(const ResampleParams& R, int lane) {
+  const int M = R.M, sd = R.sd;
+  const bool mine = lane < M;
+  const bool resample = R.mode != MMF_RESAMPLE_NONE;
+  // ---- normalise ---------------------------------------------------------------------------------------------------------
+  const float lraw = mine ? R.logw_unnorm[lane] : -INFINITY;
+  const float mx = warp_max(lraw);
+  const float shift = (mx == -INFINITY || mx == INFINITY) ? 0.0f : mx;
+  float s = 0.0f;
+  if (mine) s += expf(lraw - shift);
+  s = warp_sum(s);
+  const float lse = shift + logf(s);
+  const float l = lraw - lse;  // normalised log-weight of my particle
+  // ---- estimate ----------------------------------------------------------------------------------------------------------
+  float x[MMF_MAX_SD];
+#pragma unroll
+  for (int d = 0; d < MMF_MAX_SD; ++d) x[d] = (mine && d < sd) ? R.states[lane * sd + d] : 0.0f;
+  if (mine && !resample) R.logw_out[lane] = l;
+  if (R.estimation == MMF_ESTIMATE_WEIGHTED_AVERAGE) {
+    const float wgt = mine ? expf(l) : 0.0f;
+#pragma unroll
+    for (int d = 0; d < MMF_MAX_SD; ++d) {
+      if (d < sd) {
+        float acc = 0.0f;
+        if (mine) acc = fmaf(wgt, x[d], acc);
+        const float v = warp_sum(acc);
+        if (lane == 0) R.est_out[d] = v;
+      }
+    }
+  } else {
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    if (mine && l > best) {
+      best = l;
+      best_i = lane;
+    }
+    const float gbest = warp_max(best);
+    int cand = (best == gbest) ? best_i : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    const int win = cand == 0x7fffffff ? 0 : cand;
+    if (lane < sd) R.est_out[lane] = R.states[win * sd + lane];
+  }
+  if (!resample) return;
+  // ---- pinned softmax numerators and the strict (sequential) CDF ---------------------------------------------------------------
+  const float lmax = warp_max(mine ? l : -INFINITY);
+  const float e = mine ? exp_pinned(l - lmax) : 0.0f;
+  float run = 0.0f, c = 0.0f;
+  for (int k = 0; k < M; ++k) {
+    run = __fadd_rn(run, __shfl_sync(0xffffffffu, e, k));
+    if (lane == k) c = run;
+  }
+  const float total = run;  // c_{M-1}
+  // ---- inverse CDF of my draw + gather ----------------------------------------------------------------------------------
+  const bool systematic = R.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT;
+  double u = 0.5;
+  if (mine) u = systematic ? (R.uniforms[0] + (double)lane) / (double)R.M_out : R.uniforms[lane];
+  const float cstar = cdf_threshold(total, u);
+  int idx = 0;
+  for (int k = 0; k < M; ++k) idx += __shfl_sync(0xffffffffu, c, k) < cstar ? 1 : 0;
+  idx = idx < M - 1 ? idx : M - 1;
+  float sv[MMF_MAX_SD];
+#pragma unroll
+  for (int d = 0; d < MMF_MAX_SD; ++d) sv[d] = (mine && d < sd) ? R.states[idx * sd + d] : 0.0f;
+  if (mine) {
+#pragma unroll
+    for (int d = 0; d < MMF_MAX_SD; ++d)
+      if (d < sd) R.states_out[lane * sd + d] = sv[d];
+    R.logw_out[lane] = -logf((float)M);
+  }
+}
+
 template <int CH, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) k_pf_loop_small(const __grid_constant__ LoopParams P) {
   constexpr int LS_THREADS = NW * 32;
@@ -123,7 +211,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_pf_loop_small(const __grid_const
   R.N = P.N; R.M = M; R.sd = sd; R.M_out = M;
   R.estimation = P.estimation; R.mode = P.mode; R.alpha = 1.0f;
   R.logits_in = nullptr; R.logw_norm_out = nullptr; R.logits_out = nullptr; R.idx_out = nullptr;
-  R.logw_unnorm = P.logw_ws; R.logw_out = P.logw;
+  R.N = 1;  // nr_trajectory / nr_small are called with n = 0 on pointers that already address this trajectory
+  R.logw_unnorm = P.logw_ws + base; R.logw_out = P.logw + base;
   const bool resample = P.mode != MMF_RESAMPLE_NONE;
   const bool systematic = P.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT || P.mode == MMF_RESAMPLE_SYSTEMATIC_FAST;
 
@@ -316,11 +405,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_pf_loop_small(const __grid_const
     // ---- normalise, estimate, resample + gather: warp 0, the arithmetic of k_normalize_resample ------------------------
     __syncthreads();  // moved particles and un-normalised log-weights of all chunks are in (L1-coherent) global memory
     if (warp == 0) {
-      R.states = moved;
-      R.uniforms = P.uniforms ? P.uniforms + (size_t)t * (systematic ? (size_t)P.N : (size_t)P.N * M) : nullptr;
-      R.states_out = resample ? cur : nullptr;
-      R.est_out = P.est_out + (size_t)t * P.N * sd;
-      nr_trajectory<32>(R, n, nrs, nullptr, nullptr);
+      R.states = moved + base * sd;
+      R.uniforms = P.uniforms ? P.uniforms + (size_t)t * (systematic ? (size_t)P.N : (size_t)P.N * M) +
+                                    (systematic ? (size_t)n : base) : nullptr;
+      R.states_out = resample ? cur + base * sd : nullptr;
+      R.est_out = P.est_out + ((size_t)t * P.N + n) * sd;
+      if (nr_small_applies(R)) nr_small(R, lane); else nr_trajectory<32>(R, 0, nrs, nullptr, nullptr);
     }
     if (!resample) {  // the moved set IS the next step's input
       float* tmp = cur; cur = moved; moved = tmp;
@@ -748,7 +838,7 @@ __global__ void __launch_bounds__(128 * CH, 1) k_pf_loop_small_mma(const __grid_
                                     (systematic ? (size_t)n : base) : nullptr;
       R.states_out = resample ? cur : nullptr;
       R.est_out = P.est_out + ((size_t)step * P.N + n) * sd;
-      nr_trajectory<32>(R, 0, nrs, nullptr, nullptr);
+      if (nr_small_applies(R)) nr_small(R, lane); else nr_trajectory<32>(R, 0, nrs, nullptr, nullptr);
     }
     if (!resample) {
       float* tmp = cur; cur = moved; moved = tmp;

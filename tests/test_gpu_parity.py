@@ -798,6 +798,7 @@ def test_kf_fuse_measurements_matches_the_reference_expressions(K, sd, rows):
     ("PushCrossmodalParticleFilter", 30, "multinomial", "weighted_average"),
     ("PushCrossmodalParticleFilter", 30, "systematic", "weighted_average"),
     ("PushCrossmodalParticleFilter", 30, None, "weighted_average"),       # training-style: no resampling
+    ("PushCrossmodalParticleFilter", 17, "multinomial", "argmax"),
     ("PushUnimodalParticleFilter", 57, "multinomial", "argmax"),          # two particle chunks, ragged
     ("DoorCrossmodalParticleFilter", 128, "multinomial", "weighted_average"),  # four chunks, state_dim 3
     ("PushParticleFilter", 30, "multinomial_fast", "weighted_average"),
