@@ -57,7 +57,7 @@ int launch_ekf(const EkfParams& P, int sd, cudaStream_t stream);
 int launch_reweight_train(int N, int M, int K, int sd, uint32_t enabled, const float* ll, const float* w, const float* logw_in,
                           const float* states, float* logw_out, float* est_out, const float* d_est, const float* d_logw,
                           float* d_ll, float* d_w, float* d_logw_in, bool backward, cudaStream_t stream);
-bool resample_big_applies(int M, bool soft);
+bool resample_big_applies(int N, int M, bool soft);
 size_t resample_big_workspace_bytes(int N, int M);
 int launch_resample_big(const ResampleParams& P, void* workspace, cudaStream_t stream);
 bool pf_loop_small_applies(int N, int M);

@@ -410,7 +410,7 @@ constexpr int WS_CTAS_PER_SM = 4;
 size_t resample_workspace_bytes(int N, int M) {
   size_t window = 0;
   if (resample_window(&window) != MMF_OK) window = 200 * 1024;
-  const size_t big = resample_big_applies(M, false) ? resample_big_workspace_bytes(N, M) : 0;  // multi-pass path (resample_big.cu)
+  const size_t big = resample_big_applies(N, M, false) ? resample_big_workspace_bytes(N, M) : 0;  // multi-pass path (resample_big.cu)
   if (resample_smem_bytes(M, true) <= window) return big;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -433,7 +433,7 @@ int launch_normalize_resample(const ResampleParams& P, void* workspace, cudaStre
     if (P.M <= 1024) return launch_resample_fast<4>(P, sms, stream);
     return launch_resample_fast<8>(P, sms, stream);
   }
-  if (resample_big_applies(P.M, soft)) return launch_resample_big(P, workspace, stream);  // long trajectories: multi-pass
+  if (resample_big_applies(P.N, P.M, soft)) return launch_resample_big(P, workspace, stream);  // long trajectories: multi-pass
   const size_t smem = resample_smem_bytes(P.M, soft);
   size_t window = 0;
   int rc = resample_window(&window);

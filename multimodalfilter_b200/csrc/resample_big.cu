@@ -1,5 +1,5 @@
-// resample_big.cu -- R6 (normalise, estimate) + R7 (resample, gather) for LONG trajectories (M > 16 K particles: the upper
-// half of BASELINE config C5's sweep, 64 K ... 1 M particles per trajectory).
+// resample_big.cu -- R6 (normalise, estimate) + R7 (resample, gather) for LONG trajectories (M > 2048 particles: BASELINE
+// config C5's sweep from 4 K to 1 M particles per trajectory).
 //
 // The CTA-per-trajectory kernel (normalize_resample.cu) walks a whole trajectory with 256 threads: at M = 1 M and the 128
 // trajectories a C5 tile holds that is 128 CTAs making ~8 dependent passes over 4 MB each -- 65 ms per step, 66 GB/s, half
@@ -456,7 +456,9 @@ __global__ void __launch_bounds__(BG_TPB) k_big_search_gather(const __grid_const
   }
 }
 
-constexpr int BIG_M_MIN = 16384;  // trajectories longer than this take the multi-pass path
+constexpr int BIG_M_MIN = 2048;  // trajectories longer than the warp-per-trajectory limit take the multi-pass path (measured
+                                 // against the CTA-per-trajectory kernel: M = 4 K 5.1 vs 6.8 ms, 16 K 6.0 vs 11.3, 64 K 7.0
+                                 // vs 16.3, 256 K 8.9 vs 31.1, 1 M 12.6 vs 65.3 ms per step of 134 M particles)
 
 // MMF_RESAMPLE_BIG (read once when the library is loaded): 0 keeps the CTA-per-trajectory kernel (A/B timing), a value
 // > 1 replaces the threshold BIG_M_MIN.
@@ -469,14 +471,13 @@ static int big_threshold() {
   return t;
 }
 
-bool resample_big_applies(int M, bool soft) { return M > big_threshold() && !soft; }
+bool resample_big_applies(int N, int M, bool soft) { return M > big_threshold() && !soft && N <= 65535; }
 
 size_t resample_big_workspace_bytes(int N, int M) { return big_ws_floats(N, M) * sizeof(float); }
 
 int launch_resample_big(const ResampleParams& P, void* workspace, cudaStream_t stream) {
   MMF_REQUIRE(workspace != nullptr, "normalize_resample: M=%d needs a workspace of mmf_pf_resample_workspace_bytes() bytes", P.M);
   MMF_REQUIRE(((uintptr_t)workspace & 15) == 0, "normalize_resample: the workspace must be 16-byte aligned");
-  MMF_REQUIRE(P.N <= 65535, "normalize_resample: %d trajectories of %d particles exceed the grid (tile the trajectories)", P.N, P.M);
   const BigWs W = big_ws(static_cast<float*>(workspace), P.N, P.M);
   const bool given = P.logits_in != nullptr;
   const bool resample = P.mode != MMF_RESAMPLE_NONE;

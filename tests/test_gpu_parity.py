@@ -66,7 +66,8 @@ def test_fuse_loglik(N, M, K, weighted):
 
 # ---- R7 standalone: bit-exact indices ------------------------------------------------------------------
 RESAMPLE_CASES = [(8, 30, 30), (4, 300, 300), (6, 1000, 1000), (3, 257, 64), (2, 1, 5), (5, 2, 9), (2, 4096, 4096), (1, 10000, 777),
-                  (2, 70000, 5000), (1, 300000, 1000)]  # the last two exceed shared memory: global-workspace path (config C5)
+                  (2, 70000, 5000), (1, 300000, 1000)]  # M > 2048: the multi-pass path of resample_big.cu (config C5); MMF_RESAMPLE_BIG=0
+#                                         sends them through the CTA-per-trajectory kernels instead (tools/gpu_validate.sh runs both)
 
 
 @pytest.mark.parametrize("mode", ["multinomial", "multinomial_fast", "systematic", "systematic_fast"])

@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
 timeout -k 10 2400 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee gpurun_out/test_full11.log
+MMF_RESAMPLE_BIG=0 timeout -k 10 900 python -m pytest tests -m gpu -q -k "resample or normalize" 2>&1 | tail -2 | tee gpurun_out/test_resample_cta_path.log
+MMF_PF_LOOP_SMALL=1 timeout -k 10 900 python -m pytest tests -m gpu -q -k "one_launch" 2>&1 | tail -2 | tee gpurun_out/test_loop_small_forced.log
 timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke11.log
 timeout -k 10 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -c 600 gpurun_out/bench_c3.json; tail -5 gpurun_out/bench_c3.err
 for w in c1 c2; do timeout -k 10 600 python bench.py --workload $w --steps 5 --warmup 3 > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; tail -c 300 gpurun_out/bench_$w.json; tail -3 gpurun_out/bench_$w.err; done
