@@ -92,17 +92,20 @@ class _Encoders(nn.Module):
         def build():
             prog = fused.RowProgram()
             encs = self._encoder_list()
-            base = prog.alloc(units * len(encs))
+            base = prog.alloc(units * len(encs), fresh=True)  # holds an input (the image features): never a recycled slot
             for i, (mod, enc) in enumerate(encs):
                 if mod == "image":
                     prog.input(units, slot=base + units * i)
                 else:
                     src = prog.input(enc[0].in_features)
                     prog.sequential(enc, src, enc[0].in_features, dst=base + units * i)
+                    prog.release(src, enc[0].in_features)  # the raw input is dead once its encoder has run
             first = None
             for seq, offset, width in tails:
                 src = base if offset is None else first + offset
                 slot, dim = prog.sequential(seq, src, width)
+                if offset is None and src == base:
+                    prog.release(base, units * len(encs))  # the concatenated features: consumed by the first tail only
                 first = slot if first is None else first
                 if offset is not None or len(tails) == 1:
                     prog.output(slot, dim)

@@ -204,13 +204,14 @@ class _HeadSpec:
         """Encoders of the non-image modalities + the concatenation as one mmf_row_mlp launch; the image features
         (CNN trunk kernel + Linear tail) enter as an input."""
         prog = RowProgram()
-        base = prog.alloc(self.feat_dim)
+        base = prog.alloc(self.feat_dim, fresh=True)
         for i, (key, enc) in enumerate(self.encoders):
             if key == "image":
                 prog.input(U, slot=base + U * i)
             else:
                 src = prog.input(enc[0].in_features)
                 prog.sequential(enc, src, enc[0].in_features, dst=base + U * i)
+                prog.release(src, enc[0].in_features)
         prog.output(base, self.feat_dim)
         return prog
 
@@ -412,13 +413,34 @@ class RowProgram:
         self.ops, self.params, self._w_floats, self.scratch = [], [], 0, 0
         self.in_slots, self.in_dims, self.out_slots, self.out_dims = [], [], [], []
         self._packed = None
+        self._free = []  # (slot, size) of dead temporaries: the per-row scratch lives in shared memory, so it is reused
 
-    def alloc(self, dim: int) -> int:
-        slot, self.scratch = self.scratch, self.scratch + ((dim + 3) // 4) * 4
+    def alloc(self, dim: int, fresh: bool = False) -> int:
+        """A scratch slot; ``fresh`` = never a recycled one (program inputs: they are all written before the first op runs)."""
+        size = ((dim + 3) // 4) * 4
+        fits = [] if fresh else [f for f in self._free if f[1] >= size]
+        if fits:
+            slot, have = min(fits, key=lambda f: f[1])
+            self._free.remove((slot, have))
+            if have > size:
+                self._free.append((slot + size, have - size))
+            return slot
+        slot, self.scratch = self.scratch, self.scratch + size
         return slot
 
+    def release(self, slot: int, dim: int) -> None:
+        """A temporary nobody reads any more (the kernel requires dst to differ from src / res of the SAME op only)."""
+        self._free.append((slot, ((dim + 3) // 4) * 4))
+        merged = []
+        for start, size in sorted(self._free):  # coalesce neighbours: two dead 64-wide slots hold a 128-wide layer
+            if merged and merged[-1][0] + merged[-1][1] == start:
+                merged[-1] = (merged[-1][0], merged[-1][1] + size)
+            else:
+                merged.append((start, size))
+        self._free = merged
+
     def input(self, dim: int, slot: int = None) -> int:
-        slot = self.alloc(dim) if slot is None else slot
+        slot = self.alloc(dim, fresh=True) if slot is None else slot
         self.in_slots.append(slot)
         self.in_dims.append(dim)
         return slot
@@ -446,6 +468,17 @@ class RowProgram:
         Returns (slot, dim) of the result."""
         mods = list(seq)
         cur, dim, i = src, src_dim, 0
+        mine = set()  # temporaries this call allocated: dead once the next op has consumed them
+
+        def advance(new, new_dim, *dead):
+            for slot, d in dead:
+                if slot in mine:
+                    mine.discard(slot)
+                    self.release(slot, d)
+            if dst is None or new != dst:
+                mine.add(new)
+            return new, new_dim
+
         while i < len(mods):
             m = mods[i]
             last = lambda consumed: i + consumed >= len(mods)  # noqa: E731
@@ -457,18 +490,22 @@ class RowProgram:
                     act, used = _lib.MLP_RELU, 2
                 elif i + 1 < len(mods) and isinstance(mods[i + 1], nn.Sigmoid):
                     act, used = _lib.MLP_SIGMOID, 2
-                cur = self._linear(m, cur, act, dst=dst if last(used) else None)
-                dim, i = m.out_features, i + used
+                new = self._linear(m, cur, act, dst=dst if last(used) else None)
+                cur, dim = advance(new, m.out_features, (cur, dim))
+                i += used
             elif isinstance(getattr(m, "block1", None), nn.Linear) and isinstance(getattr(m, "block2", None), nn.Linear):
                 act = getattr(m, "activation", None)
                 if (act is not None and not isinstance(act, nn.ReLU)) or m.block1.in_features != dim \
                         or m.block2.out_features != dim or m.block1.out_features != m.block2.in_features:
                     raise NotFusable("unsupported residual block")
                 t = self._linear(m.block1, cur, _lib.MLP_RELU)
-                cur = self._linear(m.block2, t, _lib.MLP_RELU, res=cur, dst=dst if last(1) else None)
+                mine.add(t)
+                new = self._linear(m.block2, t, _lib.MLP_RELU, res=cur, dst=dst if last(1) else None)
+                cur, dim = advance(new, dim, (t, m.block1.out_features), (cur, dim))
                 i += 1
             else:
                 raise NotFusable(f"unsupported module {type(m).__name__}")
+        mine.discard(cur)  # the result stays live: it belongs to the caller
         return cur, dim
 
     def _weights(self, device):
