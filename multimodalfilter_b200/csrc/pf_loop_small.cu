@@ -8,14 +8,18 @@
 //   predict (dynamics chain) -> K measurement heads -> fusion -> normalise -> estimate -> resample + gather
 // with the particle set in shared / L1-resident global memory and no grid-wide synchronisation at all.
 //
-// The chains run on the CUDA cores in fp32 (this is the strict-parity arithmetic of particle_chain_ffma.cu: same
-// accumulation order, so the two produce identical bits): 16 warps, warp = (particle chunk of 32, block of OPW output
-// features), lane = particle.  A lane keeps its particle's 64 input activations in registers, the weights of the current
-// layer are warp-broadcast LDS.128 reads, two FMAs per FFMA2 instruction.  The layers' weights (16.6 KB each, fp32 pack
-// of mmf_chain) stream through a double buffer in shared memory by cp.async, one layer ahead of the arithmetic; one
-// __syncthreads per layer exchanges the activations (two ping-pong buffers, layout [feature / 4][particle][4]).
-// Normalise / estimate / resample is nr_trajectory<32> of normalize_resample.cuh, run by warp 0: the pinned arithmetic and
-// therefore the indices are those of k_normalize_resample bit for bit.
+// Two variants (launch_pf_loop_small picks by precision):
+//   k_pf_loop_small      MMF_PREC_FP32: the chains on the CUDA cores in exactly the accumulation order of
+//                        particle_chain_ffma.cu, so the one-launch and the per-step fp32 paths produce identical bits.
+//                        NW (default 8) warps, warp = (particle chunk of 32, block of OPW output features), lane = particle;
+//                        a lane keeps its particle's 64 input activations in registers, the weights of the current layer
+//                        are warp-broadcast LDS.128 reads, two FMAs per FFMA2.  A layer's weights (16.6 KB, fp32 pack of
+//                        mmf_chain) are fetched by cp.async into a 4-deep ring three layers ahead; one __syncthreads per
+//                        layer exchanges the activations (two ping-pong buffers, layout [feature / 4][particle][4]).
+//   k_pf_loop_small_mma  MMF_PREC_BF16X3 / BF16: the layers on mma.sync with split bf16 operands (further down).
+// Normalise / estimate / resample is nr_trajectory<32> of normalize_resample.cuh -- for M <= 32 its register-resident
+// twin nr_small -- run by warp 0: the pinned arithmetic and therefore the indices are those of k_normalize_resample bit
+// for bit.
 #include "normalize_resample.cuh"
 #include "tc_common.cuh"
 
