@@ -472,9 +472,12 @@ __device__ __forceinline__ void split_pair(float2 v, uint32_t& hi, uint32_t& lo)
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
 }
 
-template <int CH>
-__global__ void __launch_bounds__(128 * CH, 1) k_pf_loop_small_mma(const __grid_constant__ LoopParams P) {
-  constexpr int THREADS = 128 * CH, MP = 32 * CH;
+// NT = n-tiles (8 output features each) per warp: 2 -> 4 warps per particle chunk, 1 -> 8 warps per chunk (two warps per
+// scheduler hide each other's ldmatrix / HMMA latency; every warp then re-reads the chunk's A operand).
+template <int CH, int NT>
+__global__ void __launch_bounds__(256 * CH / NT, 1) k_pf_loop_small_mma(const __grid_constant__ LoopParams P) {
+  constexpr int NQ = 8 / NT;  // warps per particle chunk
+  constexpr int THREADS = 32 * NQ * CH, MP = 32 * CH;
   constexpr int RING_B = 2 * TILE_B;  // bytes of one layer: hi tile | lo tile
   extern __shared__ __align__(1024) uint8_t smb[];
   __shared__ const uint8_t* ring_src[LS_MAX_STAGES];
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(128 * CH, 1) k_pf_loop_small_mma(const __grid_
 
   const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int chunk = warp >> 2, nq = warp & 3;
+  const int chunk = warp / NQ, nq = warp % NQ;
   const int n = blockIdx.x;
   const int M = P.M, sd = P.sd, T = P.T;
   const size_t base = (size_t)n * M;
@@ -614,7 +617,9 @@ __global__ void __launch_bounds__(128 * CH, 1) k_pf_loop_small_mma(const __grid_
       }
     }
     int ab = 0;
-    float2 rb[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};  // this thread's columns of the chain's per-trajectory row
+    float2 rb[NT];  // this thread's columns of the chain's per-trajectory row
+#pragma unroll
+    for (int j = 0; j < NT; ++j) rb[j] = make_float2(0.f, 0.f);
     float mw = 0.0f;
 
     for (int gi = 0; gi < G; ++gi) {
@@ -641,9 +646,9 @@ __global__ void __launch_bounds__(128 * CH, 1) k_pf_loop_small_mma(const __grid_
       if (kind == LS_IN) {
         // ---- input layer on the CUDA cores: relu(in_W x + in_b) for this thread's 4 rows x 4 columns ---------------------------
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < NT; ++j)
           rb[j] = __ldg(reinterpret_cast<const float2*>(P.rowbias + ((size_t)c * T * P.N + (size_t)step * P.N + n) * U +
-                                                        8 * (2 * nq + j) + 2 * t));
+                                                        8 * (NT * nq + j) + 2 * t));
         if (c > 0) mw = P.modw != nullptr ? __ldg(P.modw + ((size_t)step * P.N + n) * P.K + (c - 1)) : 0.0f;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -661,8 +666,8 @@ __global__ void __launch_bounds__(128 * CH, 1) k_pf_loop_small_mma(const __grid_
               xi[0] = xv.x; xi[1] = xv.y; xi[2] = xv.z; xi[3] = xv.w;
             }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int col = 8 * (2 * nq + j) + 2 * t;
+            for (int j = 0; j < NT; ++j) {
+              const int col = 8 * (NT * nq + j) + 2 * t;
               float2 v = *reinterpret_cast<const float2*>(in_b + col);
 #pragma unroll
               for (int i = 0; i < MMF_MAX_SD; ++i) {
@@ -683,36 +688,42 @@ __global__ void __launch_bounds__(128 * CH, 1) k_pf_loop_small_mma(const __grid_
         // ---- 64 -> 64 layer: 2 m-tiles x 2 n-tiles per warp, K = 64 in four k16 steps, split operands ----------------------------
         const uint32_t a_hi = smem_u32(plane(ab)), a_lo = a_hi + MP * LM_AST * 4;
         const uint32_t w_hi = smem_u32(wt), w_lo = w_hi + TILE_B;
-        float acc[2][2][4];
+        float acc[2][NT][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
+          for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[mt][j][e] = 0.0f;
         const int lm = lane >> 3, lr = lane & 7;  // ldmatrix: this lane addresses row lr of matrix lm
+        uint32_t bh[4], bl[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          uint32_t ah[2][4], al[2][4], bh[4], bl[4];
+          uint32_t ah[2][4], al[2][4];
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             const uint32_t off = (uint32_t)(((chunk * 32 + mt * 16 + (lm & 1) * 8 + lr) * LM_AST + 8 * s + (lm >> 1) * 4) * 4);
             ldmatrix_x4(ah[mt], a_hi + off);
             if (!single_pass) ldmatrix_x4(al[mt], a_lo + off);
           }
-          {  // matrices: (n-tile 2 nq, k chunk 2 s), (2 nq, 2 s + 1), (2 nq + 1, 2 s), (2 nq + 1, 2 s + 1)
+          if (NT == 2) {  // matrices: (n-tile 2 nq, k chunk 2 s), (2 nq, 2 s + 1), (2 nq + 1, 2 s), (2 nq + 1, 2 s + 1)
             const uint32_t off = (uint32_t)((2 * nq + (lm >> 1)) * 1024 + lr * 128 + (((2 * s + (lm & 1)) ^ lr) << 4));
+            ldmatrix_x4(bh, w_hi + off);
+            if (!single_pass) ldmatrix_x4(bl, w_lo + off);
+          } else if ((s & 1) == 0) {  // one n-tile: the k chunks 2 s .. 2 s + 3 of two steps in one load
+            const uint32_t off = (uint32_t)(nq * 1024 + lr * 128 + (((2 * s + lm) ^ lr) << 4));
             ldmatrix_x4(bh, w_hi + off);
             if (!single_pass) ldmatrix_x4(bl, w_lo + off);
           }
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              mma_bf16(acc[mt][j], ah[mt], bh[2 * j], bh[2 * j + 1]);
+            for (int j = 0; j < NT; ++j) {
+              const int q = NT == 2 ? 2 * j : 2 * (s & 1);  // registers of this (n-tile, step) in bh / bl
+              mma_bf16(acc[mt][j], ah[mt], bh[q], bh[q + 1]);
               if (!single_pass) {
-                mma_bf16(acc[mt][j], ah[mt], bl[2 * j], bl[2 * j + 1]);
-                mma_bf16(acc[mt][j], al[mt], bh[2 * j], bh[2 * j + 1]);
+                mma_bf16(acc[mt][j], ah[mt], bl[q], bl[q + 1]);
+                mma_bf16(acc[mt][j], al[mt], bh[q], bh[q + 1]);
               }
             }
           }
@@ -721,8 +732,8 @@ __global__ void __launch_bounds__(128 * CH, 1) k_pf_loop_small_mma(const __grid_
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int col = 8 * (2 * nq + j) + 2 * t;
+          for (int j = 0; j < NT; ++j) {
+            const int col = 8 * (NT * nq + j) + 2 * t;
             const float2 b = kind == LS_MID ? rb[j] : *reinterpret_cast<const float2*>(biases + layer * U + col);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -898,20 +909,20 @@ static size_t mma_smem_bytes(int ch, int M) {
 }
 
 // returns MMF_OK, an error, or -1 when the shared-memory window is too small for this shape (caller: CUDA-core variant)
-template <int CH>
+template <int CH, int NT>
 static int launch_ls_mma(const LoopParams& P, int M, cudaStream_t stream) {
   static thread_local int configured_dev = -1;
   static thread_local size_t window = 0;
   int dev = 0;
   MMF_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    int rc = opt_in_shared_memory(k_pf_loop_small_mma<CH>, &window);
+    int rc = opt_in_shared_memory(k_pf_loop_small_mma<CH, NT>, &window);
     if (rc) return rc;
     configured_dev = dev;
   }
   const size_t smem = mma_smem_bytes(CH, M);
   if (smem > window) return -1;
-  k_pf_loop_small_mma<CH><<<P.N, 128 * CH, smem, stream>>>(P);
+  k_pf_loop_small_mma<CH, NT><<<P.N, 256 * CH / NT, smem, stream>>>(P);
   MMF_LAUNCH_CHECK("k_pf_loop_small_mma");
   return MMF_OK;
 }
@@ -946,7 +957,13 @@ int launch_pf_loop_small(const mmf_pf_model* model, int T, int N, int M, float* 
   for (int i = 0; i < MMF_MAX_SD * MMF_MAX_SD; ++i) P.q[i] = model->q_tril[i];
   const int ch = M <= 32 ? 1 : (M <= 64 ? 2 : 4);
   if (precision != MMF_PREC_FP32 && have_images && tails_fit) {  // tensor-core variant (split bf16 operands)
-    int rc = ch == 1 ? launch_ls_mma<1>(P, M, stream) : ch == 2 ? launch_ls_mma<2>(P, M, stream) : launch_ls_mma<4>(P, M, stream);
+    // M <= 32: eight warps of one n-tile each (MMF_LS_NT=2 keeps four warps of two n-tiles, for A/B timing)
+    static const int nt1 = [] {
+      const char* env = getenv("MMF_LS_NT");
+      return env == nullptr || atoi(env) == 1;
+    }();
+    int rc = ch == 1 ? (nt1 ? launch_ls_mma<1, 1>(P, M, stream) : launch_ls_mma<1, 2>(P, M, stream))
+             : ch == 2 ? launch_ls_mma<2, 2>(P, M, stream) : launch_ls_mma<4, 2>(P, M, stream);
     if (rc != -1) return rc;
   }
   const size_t floats = (size_t)LS_NBUF * LS_WMAX + 2 * (size_t)U * 32 * ch + (size_t)32 * ch * 4 + trajectory_scratch_floats(M, false);
