@@ -259,3 +259,79 @@ def test_chunk_major_rows_view_round_trip():
     planes = rows.reshape(5, 16, 4).transpose(0, 1).contiguous()        # (16, 5, 4)
     assert torch.equal(ops.rows_view(planes), rows)
     assert torch.equal(ops.rows_view(planes[None, None]), rows[None, None])
+
+
+def test_row_programs_recycle_scratch_without_hazards():
+    """fused.RowProgram recycles dead scratch slots (the per-row scratch lives in shared memory and decides the kernel's
+    occupancy).  Executed symbolically here: every op must read values produced by the intended writer -- an input or an
+    earlier op -- that no later op has overwritten in between, dst must not overlap src / res of its own op, and inputs
+    must never sit in a recycled slot (all inputs are written before the first op runs)."""
+    import numpy as np
+    import torch
+
+    from multimodalfilter_b200 import fused
+    from multimodalfilter_b200.crossmodal import models as M
+
+    def programs():
+        m = M.DoorVirtualSensorModel()
+        yield "door virtual sensor", m.encoded_program("sensor", [(m.shared_layers, None, m.units * len(m.modalities)),
+                                                                    (m.z_layer, 0, m.units), (m.r_layer, m.units, m.units)]), m
+        m = M.PushVirtualSensorModel(modalities={"pos", "sensors"})
+        yield "push virtual sensor", m.encoded_program("sensor", [(m.shared_layers, None, m.units * len(m.modalities)),
+                                                                    (m.z_layer, 0, m.units), (m.r_layer, m.units, m.units)]), m
+        m = M.DoorCrossmodalKalmanFilterWeightModel(state_dim=3)
+        yield "KF weight model", m.encoded_program("weights", [(m.fusion_layers, None, 3 * 64)]), m
+        m = M.PushCrossmodalWeightModel(know_image_blackout=False)
+        yield "PF weight model", m.encoded_program("weights", [(m.fusion_layers, None, 3 * 64)]), m
+        f = M.PushCrossmodalParticleFilter()
+        for h in fused.PFPlan.build(f).heads:
+            yield "head features", h._feature_program(), None
+
+    for name, prog, _ in programs():
+        assert prog is not None, name
+        # numeric execution of the program on the host (numpy) against the slot-free evaluation of the same ops
+        rng = np.random.default_rng(0)
+        S = np.full(prog.scratch, np.nan)
+        for slot, d in zip(prog.in_slots, prog.in_dims):
+            assert np.isnan(S[slot:slot + d]).all(), f"{name}: two inputs share scratch"
+            S[slot:slot + d] = rng.standard_normal(d)
+        values = {}  # (slot, dim) -> the vector the most recent writer put there
+        for slot, d in zip(prog.in_slots, prog.in_dims):
+            values[(slot, d)] = S[slot:slot + d].copy()
+        for j, (op, lin) in enumerate(zip(prog.ops, prog.params)):
+            assert op.dst + op.out_dim <= op.src or op.src + op.in_dim <= op.dst, f"{name}: op {j} dst overlaps src"
+            assert op.res < 0 or op.dst + op.out_dim <= op.res or op.res + op.out_dim <= op.dst, f"{name}: op {j} dst overlaps res"
+            x = S[op.src:op.src + op.in_dim]
+            assert not np.isnan(x).any(), f"{name}: op {j} reads scratch nobody wrote"
+            W = lin.weight.detach().double().numpy()
+            y = W @ x + lin.bias.detach().double().numpy()
+            if op.res >= 0:
+                r = S[op.res:op.res + op.out_dim]
+                assert not np.isnan(r).any(), f"{name}: op {j} reads a residual nobody wrote"
+                y = y + r
+            if op.act == 1:
+                y = np.maximum(y, 0.0)
+            elif op.act == 2:
+                y = 1.0 / (1.0 + np.exp(-y))
+            S[op.dst:op.dst + op.out_dim] = y
+        for slot, d in zip(prog.out_slots, prog.out_dims):
+            assert not np.isnan(S[slot:slot + d]).any(), f"{name}: an output slot was never written"
+    # and the numbers: the recycled program equals the torch modules it was compiled from (one case, CPU, float64)
+    m = M.PushCrossmodalWeightModel(know_image_blackout=False).double()
+    prog = m.encoded_program("check", [(m.fusion_layers, None, 3 * 64)])
+    obs = {"gripper_pos": torch.randn(1, 3, dtype=torch.float64), "gripper_sensors": torch.randn(1, 7, dtype=torch.float64),
+           "image": torch.randn(1, 32, 32, dtype=torch.float64)}
+    with torch.no_grad():
+        ins = [enc(obs["image"][:, None]) if mod == "image" else obs[fused.OBS_KEY[mod]] for mod, enc in m._encoder_list()]
+        ref = m.fusion_layers(m.encode(obs))[0].numpy()
+    S = np.zeros(prog.scratch)
+    for slot, d, x in zip(prog.in_slots, prog.in_dims, ins):
+        S[slot:slot + d] = x[0].numpy()
+    for op, lin in zip(prog.ops, prog.params):
+        y = lin.weight.detach().numpy() @ S[op.src:op.src + op.in_dim] + lin.bias.detach().numpy()
+        if op.res >= 0:
+            y = y + S[op.res:op.res + op.out_dim]
+        y = np.maximum(y, 0.0) if op.act == 1 else (1.0 / (1.0 + np.exp(-y)) if op.act == 2 else y)
+        S[op.dst:op.dst + op.out_dim] = y
+    got = S[prog.out_slots[0]:prog.out_slots[0] + prog.out_dims[0]]
+    assert np.allclose(got, ref, rtol=1e-10, atol=1e-12), np.abs(got - ref).max()
