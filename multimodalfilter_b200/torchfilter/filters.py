@@ -302,7 +302,7 @@ class ParticleFilter(Filter):
         if _needs_grad(self, self.particle_states, self.particle_log_weights):
             resample, _ = self._modes()
             T, N = controls.shape[:2]
-            if (not controls.is_cuda or not training.fused_train_applicable(self, plan, resample)
+            if (T == 0 or not controls.is_cuda or not training.fused_train_applicable(self, plan, resample)
                     or self.num_particles != self.particle_states.shape[1]
                     or not all(isinstance(v, torch.Tensor) and v.is_cuda for v in observations.values())):
                 return super().forward_loop(observations=observations, controls=controls)
