@@ -8,6 +8,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from multimodalfilter_b200.distributed import (
+    FlatGradients,
+    StreamAllReduce,
     allreduce_gradients,
     gather_estimates,
     max_over_ranks,
@@ -52,6 +54,33 @@ def _worker(rank, world, port, tmp):
         for p in lin.parameters():
             assert torch.allclose(p.grad, torch.full_like(p, (1 + world) / 2.0))
         assert max_over_ranks(10.0 + rank, "cpu") == 10.0 + world - 1
+        # the training step's exchange (bench.py run_c4, two-graph form): parameter gradients are views into ONE flat
+        # buffer; backward accumulates into the views, one all-reduce of the buffer, scale, optimiser step on the views
+        torch.manual_seed(7)  # identical replicas on both ranks
+        net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.ReLU(), torch.nn.Linear(4, 2))
+        flat = FlatGradients(net.parameters())
+        assert flat.flat.numel() == sum(p.numel() for p in net.parameters()) and flat.intact()
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        xs = torch.randn(world, 6, 5, generator=torch.Generator().manual_seed(3))  # one shard of the batch per rank
+        flat.zero()
+        net(xs[rank]).pow(2).mean().backward()
+        assert flat.intact(), "backward replaced a gradient view"
+        local = flat.flat.clone()
+        dist.all_reduce(flat.flat, op=dist.ReduceOp.SUM)
+        flat.flat.mul_(1.0 / world)
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        assert torch.allclose(flat.flat, torch.stack(gathered).mean(dim=0), rtol=1e-6, atol=1e-8)
+        before = [p.detach().clone() for p in net.parameters()]
+        opt.step()
+        for p, b in zip(net.parameters(), before):  # the optimiser saw the averaged gradient through the views
+            assert torch.allclose(p.detach(), b - 0.1 * p.grad)
+        after = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        both = [torch.empty_like(after) for _ in range(world)]
+        dist.all_gather(both, after)
+        assert torch.equal(both[0], both[1]), "replicas diverged after the exchanged step"
+        with pytest.raises(AssertionError):  # the stream-ordered NCCL path refuses a CPU device instead of falling back
+            StreamAllReduce(torch.device("cpu"))
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
