@@ -177,8 +177,11 @@ int mmf_pf_forward_loop_persistent(int32_t N, int32_t M);
  *   resample_mode == NONE: states_out may be NULL (states stay where they are), logw_out (N,M).
  * uniforms: float64, (N, M_out) for MULTINOMIAL_*, (N) for SYSTEMATIC_*.
  * Optional outputs (NULL to skip): logw_norm_out (N,M), logits_out (N,M), idx_out (N,M_out) int64.
- * workspace: mmf_pf_resample_workspace_bytes(N, M) bytes (only touched when M does not fit the
- * shared-memory path). */
+ * workspace: mmf_pf_resample_workspace_bytes(N, M) bytes, 16-byte aligned; 0 (workspace may be NULL) for M <= 2048, where a
+ * warp owns a trajectory in shared memory.  Longer trajectories take a multi-pass path over (chunk of 4096 particles,
+ * trajectory) grids whose CDF lives in the workspace (4 (M + ~0.1 M) + 32 K bytes per trajectory; resample_big.cu);
+ * environment MMF_RESAMPLE_BIG, read once when the library is loaded: 0 = CTA-per-trajectory kernels instead, n > 1 =
+ * multi-pass from M > n. */
 size_t mmf_pf_resample_workspace_bytes(int32_t N, int32_t M);
 int mmf_pf_normalize_resample(int32_t N, int32_t M, int32_t sd, const float* states,
                               const float* logw_unnorm, int32_t estimation_method,
