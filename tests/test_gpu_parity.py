@@ -916,3 +916,35 @@ def test_reweight_train_kernels_match_torch_autograd(K, mask, with_w, M_):
             off = [k for k in range(K) if k not in on]
             assert all(float(q[k].abs().max()) == 0.0 for k in off), "gradient leaked into a disabled head"
         assert_close(q, r, 2e-5, atol=1e-6, msg=name)
+
+
+def test_forward_loop_with_long_trajectories():
+    """M = 3000 particles per trajectory: normalise / resample goes through the multi-pass path (resample_big.cu), from the
+    whole-sequence call and from the per-step path alike -- identical bits between the two, and the first step's estimate
+    (no resampling upstream of it) within the bar of the oracle."""
+    name, sd, N, Mp, T = "PushUnimodalParticleFilter", 2, 3, 3000, 3
+    init, eps, us = draw_noise(T, N, Mp, sd, seed=95)
+    states, obs, controls = synthetic_trajectories(T + 1, N, sd, seed=96)
+    cov = (torch.eye(sd) * 0.1)[None].expand(N, sd, sd)
+    o = fill_parameters(getattr(port, name)(), seed=97).eval()
+    o.num_particles = Mp
+    o.noise = RecordedNoise(init_eps=init, process_eps=eps, uniforms=us, arithmetic="pinned")
+    with torch.no_grad():
+        o.initialize_beliefs(mean=states[0], covariance=cov)
+        ref = o.forward_loop(observations={k: v[1:] for k, v in obs.items()}, controls=controls[1:])
+    assert _lib.load().mmf_pf_resample_workspace_bytes(N, Mp) > 0
+    outs = []
+    for whole in (True, False):
+        p = fill_parameters(_product(name)(), seed=97).to(DEV).eval()
+        p.num_particles = Mp
+        p.whole_loop = whole
+        p.noise = ReplayNoise(init_eps=init, process_eps=list(eps), uniforms=list(us))
+        with torch.no_grad():
+            p.initialize_beliefs(mean=states[0].to(DEV), covariance=cov.to(DEV).contiguous())
+            est = p.forward_loop(observations={k: v[1:].to(DEV) for k, v in obs.items()}, controls=controls[1:].to(DEV))
+        outs.append((est.clone(), p.particle_states.clone(), p.particle_log_weights.clone()))
+    torch.cuda.synchronize()
+    (e1, s1, l1), (e0, s0, l0) = outs
+    assert torch.equal(e1, e0) and torch.equal(s1, s0) and torch.equal(l1, l0)
+    assert_close(e1[0].cpu(), ref[0], RTOL, msg="first-step estimate vs oracle")
+    assert torch.isfinite(e1).all() and float((e1.cpu() - ref).abs().max()) < 0.5 * float(ref.abs().max())
