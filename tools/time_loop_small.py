@@ -1,5 +1,5 @@
 """Times mmf_pf_forward_loop alone at config C1's shape (PushCrossmodalParticleFilter, 32 x 30 particles, 50 steps).
-Usage: [MMF_PF_LOOP_SMALL=0|1] [MMF_LS_WARPS=4|8|16] python tools/time_loop_small.py [N M T [mode]]"""
+Usage: [MMF_PF_LOOP_SMALL=0|1] [MMF_LS_NT=1|2] [PREC=bf16x3|bf16|fp32] python tools/time_loop_small.py [N M T [mode]]"""
 import os
 import sys
 
@@ -46,5 +46,5 @@ torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 10
 persistent = _lib.load().mmf_pf_forward_loop_persistent(N, Mp)
 print(f"N={N} M={Mp} T={T} {mode:18s} {prec:7s} LOOP_SMALL={os.environ.get('MMF_PF_LOOP_SMALL', 'auto'):4s} persistent={persistent} "
-      f"warps={os.environ.get('MMF_LS_WARPS', 'default'):7s}: {ms:7.3f} ms per pass, {ms * 1e3 / T:6.1f} us per filter step, "
+      f"nt={os.environ.get('MMF_LS_NT', 'default'):7s}: {ms:7.3f} ms per pass, {ms * 1e3 / T:6.1f} us per filter step, "
       f"checksum {float(est.double().sum()):.6f}")
