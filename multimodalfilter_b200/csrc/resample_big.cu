@@ -330,15 +330,17 @@ __global__ void __launch_bounds__(BG_TPB) k_big_coarse(const __grid_constant__ R
   }
 }
 
+constexpr int BNB = 4;  // draws a thread searches in lock step (8 measured slower: 128 registers, two CTAs per SM: 13.9 vs 12.6 ms at M = 1 M)
+
 // lower_bound_batch with the first levels in shared memory: `coarse[g]` = the last CDF entry of window g.  Same probes'
 // decisions, same near-tie rule (any probed entry within the band of the key sends the draw to the exact threshold).
 __device__ __forceinline__ void lower_bound_two_level(const float* cdf, const float* coarse, int G, int sl, int M, float total,
-                                                      const double (&u)[NB], int (&idx)[NB], bool monotone) {
-  float c0[NB], band[NB];
-  int lo[NB], hi[NB];
-  bool near[NB];
+                                                      const double (&u)[BNB], int (&idx)[BNB], bool monotone) {
+  float c0[BNB], band[BNB];
+  int lo[BNB], hi[BNB];
+  bool near[BNB];
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
+  for (int b = 0; b < BNB; ++b) {
     c0[b] = (float)(u[b] * (double)total);
     band[b] = fmaxf(c0[b] * 4.8e-7f, 1e-37f);
     lo[b] = 0;
@@ -348,7 +350,7 @@ __device__ __forceinline__ void lower_bound_two_level(const float* cdf, const fl
   const int it1 = 32 - __clz(G);
   for (int it = 0; it < it1; ++it) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    for (int b = 0; b < BNB; ++b) {
       const bool open = lo[b] < hi[b];
       const int mid = open ? lo[b] + ((hi[b] - lo[b]) >> 1) : 0;
       const float c = coarse[mid];
@@ -358,9 +360,9 @@ __device__ __forceinline__ void lower_bound_two_level(const float* cdf, const fl
       }
     }
   }
-  bool past[NB];  // the key lies beyond the last entry: lower bound = M
+  bool past[BNB];  // the key lies beyond the last entry: lower bound = M
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
+  for (int b = 0; b < BNB; ++b) {
     past[b] = lo[b] >= G;
     const long long first = (long long)lo[b] << sl, end = first + (1 << sl) - 1;  // the window's last entry is >= key
     lo[b] = past[b] ? M : (int)first;
@@ -368,7 +370,7 @@ __device__ __forceinline__ void lower_bound_two_level(const float* cdf, const fl
   }
   for (int it = 0; it < sl; ++it) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    for (int b = 0; b < BNB; ++b) {
       const bool open = lo[b] < hi[b];
       const int mid = open ? lo[b] + ((hi[b] - lo[b]) >> 1) : 0;
       const float c = cdf[mid];
@@ -386,7 +388,7 @@ __device__ __forceinline__ void lower_bound_two_level(const float* cdf, const fl
   // can dip by an ulp at a segment boundary, and there the definition IS the probe sequence of the full search.  A long
   // plateau of equal entries (dead particles) falls back to the full search as well.
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
+  for (int b = 0; b < BNB; ++b) {
     if (near[b]) {
       const float cstar = cdf_threshold(total, u[b]);
       int l = lo[b] < M ? lo[b] : M;
@@ -420,27 +422,27 @@ __global__ void __launch_bounds__(BG_TPB) k_big_search_gather(const __grid_const
   const float uniform_lw = -logf((float)M);
   const double u0 = systematic ? P.uniforms[n] : 0.0;
   const int j0 = blockIdx.x * BG_CHUNK;
-  for (int base = j0; base < j0 + BG_CHUNK && base < S; base += BG_TPB * NB) {
-    double u[NB];
+  for (int base = j0; base < j0 + BG_CHUNK && base < S; base += BG_TPB * BNB) {
+    double u[BNB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    for (int b = 0; b < BNB; ++b) {
       const int j = base + b * BG_TPB + tid;
       u[b] = j >= S ? 0.5 : systematic ? (u0 + (double)j) / (double)S : P.uniforms[(size_t)n * S + j];
     }
-    int idx[NB];
+    int idx[BNB];
     lower_bound_two_level(cdf, coarse, G, sl, M, total, u, idx,
                           P.mode == MMF_RESAMPLE_MULTINOMIAL_STRICT || P.mode == MMF_RESAMPLE_SYSTEMATIC_STRICT);
-    float sv[NB][MMF_MAX_SD];
+    float sv[BNB][MMF_MAX_SD];
     if (P.states_out) {
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
+      for (int b = 0; b < BNB; ++b) {
         const float* src = P.states + ((size_t)n * M + idx[b]) * sd;
 #pragma unroll
         for (int d = 0; d < MMF_MAX_SD; ++d) sv[b][d] = d < sd ? src[d] : 0.0f;
       }
     }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    for (int b = 0; b < BNB; ++b) {
       const int j = base + b * BG_TPB + tid;
       if (j < S) {
         if (P.idx_out) P.idx_out[(size_t)n * S + j] = idx[b];
